@@ -1,0 +1,1078 @@
+// lm3d_kernels.cu -- hand-written sm_100a kernels for the 2D-box -> 3D lift and the C ABI
+// declared in include/lm3d.h.  Replaces ProcessPose._3d_processing / _transform_to_global
+// (/root/reference/src/mapper/pose_processor.py:124-260) for whole sequences.
+//
+// Pipeline per lm3d_lift_boxes call (all on the caller's stream, no host sync):
+//   1. prep_frames_kernel : pose7/intr4 (fp64) -> 48-byte FrameTab per frame
+//   2. prep_boxes_kernel  : box -> frame (CSR search), clamp rect, classify small/large,
+//                           append to the two work lists
+//   3. lift_small_kernel  : persistent, ONE WARP PER BOX (rect area <= kSmallMaxPix)
+//   4. lift_large_kernel  : persistent, ONE CTA PER BOX
+// Both lift kernels are a single fused pass over the box pixels that does the unproject +
+// pose transform + min/max/sum reduction AND the counting half of an exact percentile
+// select (sample -> bracket -> count/collect), followed by an exact finish on the few
+// collected candidates in shared memory.  No sort of the box, no global histogram.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+
+#include "lm3d.h"
+#include "lm3d_device.cuh"
+
+namespace lm3d {
+
+// ------------------------------------------------------------------------------------------
+// tunables
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallMaxPix = 8192;       // warp-per-box up to this rect area
+constexpr int kSmallWarps = 8;           // warps per CTA in the small kernel
+constexpr int kSmallCap = 1536;          // candidate keys per warp (6 KB)
+constexpr int kSmallChunk = 2;           // boxes claimed per atomic
+constexpr float kBracketZ = 3.0f;        // bracket half-width in sample sigmas
+
+constexpr int kLargeThreads = 256;
+constexpr int kLargeWarps = kLargeThreads / 32;
+constexpr int kLargeCap = 23552;         // candidate keys per CTA (92 KB)
+constexpr int kSortCap = 4096;           // block bitonic capacity (16 KB)
+
+struct Workspace {
+  FrameTab* tab;        // [F]
+  int32_t* box_frame;   // [B]
+  int32_t* small_list;  // [B]
+  int32_t* large_list;  // [B]
+  int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t workspace_layout(int64_t F, int64_t B, char* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  char* c = take(64);
+  char* t = take((size_t)F * sizeof(FrameTab));
+  char* bf = take((size_t)B * 4);
+  char* sl = take((size_t)B * 4);
+  char* ll = take((size_t)B * 4);
+  if (ws) {
+    ws->counters = (int32_t*)c;
+    ws->tab = (FrameTab*)t;
+    ws->box_frame = (int32_t*)bf;
+    ws->small_list = (int32_t*)sl;
+    ws->large_list = (int32_t*)ll;
+  }
+  return off;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. frame table  (R1 already applied by the caller; R3 + R4 folded with the pinhole model)
+// ------------------------------------------------------------------------------------------
+__global__ void prep_frames_kernel(const double* __restrict__ pose7, const double* __restrict__ intr4,
+                                   int64_t F, double inv_scale, FrameTab* __restrict__ tab) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const double* p = pose7 + f * 7;
+  const double tx = p[0], ty = p[1], tz = p[2];
+  double x = p[3], y = p[4], z = p[5], w = p[6];
+  const double n = sqrt(x * x + y * y + z * z + w * w);
+  x /= n; y /= n; z /= n; w /= n;
+  double R[3][3];
+  R[0][0] = 1.0 - 2.0 * (y * y + z * z); R[0][1] = 2.0 * (x * y - z * w); R[0][2] = 2.0 * (x * z + y * w);
+  R[1][0] = 2.0 * (x * y + z * w); R[1][1] = 1.0 - 2.0 * (x * x + z * z); R[1][2] = 2.0 * (y * z - x * w);
+  R[2][0] = 2.0 * (x * z - y * w); R[2][1] = 2.0 * (y * z + x * w); R[2][2] = 1.0 - 2.0 * (x * x + y * y);
+  const double fx = intr4[f * 4 + 0], fy = intr4[f * 4 + 1], cx = intr4[f * 4 + 2], cy = intr4[f * 4 + 3];
+  FrameTab t;
+  const double tt[3] = {tx, ty, tz};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    t.a[k] = (float)(R[k][0] / fx * inv_scale);
+    t.b[k] = (float)(R[k][1] / fy * inv_scale);
+    t.c[k] = (float)((R[k][2] - R[k][0] * cx / fx - R[k][1] * cy / fy) * inv_scale);
+    t.t[k] = (float)tt[k];
+  }
+  tab[f] = t;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. boxes: frame lookup, classification, work lists
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t csr_find(const int64_t* __restrict__ off, int64_t F, int64_t b) {
+  int64_t lo = 0, hi = F;  // largest f with off[f] <= b
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= b) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64_t* __restrict__ frame_off,
+                                  int64_t F, int64_t B, int H, int W, int32_t* __restrict__ box_frame,
+                                  int32_t* __restrict__ small_list, int32_t* __restrict__ large_list,
+                                  int32_t* __restrict__ counters) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool is_small = false, is_large = false;
+  if (b < B) {
+    box_frame[b] = (int32_t)csr_find(frame_off, F, b);
+    const int4 r = reinterpret_cast<const int4*>(rect4)[b];
+    const int xa = min(max(r.x, 0), W - 1), xb = min(max(r.z, 0), W - 1);
+    const int ya = min(max(r.y, 0), H - 1), yb = min(max(r.w, 0), H - 1);
+    const int64_t area = (int64_t)(abs(xb - xa) + 1) * (abs(yb - ya) + 1);
+    is_small = area <= kSmallMaxPix;
+    is_large = !is_small;
+  }
+  // warp-aggregated, order-preserving append (keeps frame locality in the lists)
+  const uint32_t ms = __ballot_sync(kFull, is_small), ml = __ballot_sync(kFull, is_large);
+  int bs = 0, bl = 0;
+  if (lane == 0) {
+    if (ms) bs = atomicAdd(&counters[0], __popc(ms));
+    if (ml) bl = atomicAdd(&counters[1], __popc(ml));
+  }
+  bs = __shfl_sync(kFull, bs, 0);
+  bl = __shfl_sync(kFull, bl, 0);
+  const uint32_t lt = lanemask_lt();
+  if (is_small) small_list[bs + __popc(ms & lt)] = (int32_t)b;
+  if (is_large) large_list[bl + __popc(ml & lt)] = (int32_t)b;
+}
+
+__global__ void scale_boxes_kernel(const double* __restrict__ boxes, const double* __restrict__ image_wh,
+                                   const int64_t* __restrict__ frame_off, int64_t F, int64_t B, int dw, int dh,
+                                   int32_t* __restrict__ rect4) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t f = csr_find(frame_off, F, b);
+  const double iw = image_wh[f * 2 + 0], ih = image_wh[f * 2 + 1];
+  // R5: x*dw/iw in this op order (mul then div, both correctly rounded => bit-identical to numpy)
+  const double xs0 = __ddiv_rn(__dmul_rn(boxes[b * 4 + 0], (double)dw), iw);
+  const double ys0 = __ddiv_rn(__dmul_rn(boxes[b * 4 + 1], (double)dh), ih);
+  const double xs1 = __ddiv_rn(__dmul_rn(boxes[b * 4 + 2], (double)dw), iw);
+  const double ys1 = __ddiv_rn(__dmul_rn(boxes[b * 4 + 3], (double)dh), ih);
+  auto px = [](double v, int hi) {  // R6: int() truncation toward zero, then clamp
+    double t = trunc(v);
+    if (!(t == t)) t = 0.0;
+    t = fmin(fmax(t, 0.0), (double)hi);
+    return (int)t;
+  };
+  const int xa = px(xs0, dw - 1), xb = px(xs1, dw - 1), ya = px(ys0, dh - 1), yb = px(ys1, dh - 1);
+  reinterpret_cast<int4*>(rect4)[b] = make_int4(min(xa, xb), min(ya, yb), max(xa, xb), max(ya, yb));
+}
+
+// ------------------------------------------------------------------------------------------
+// shared launch parameters
+// ------------------------------------------------------------------------------------------
+struct LiftArgs {
+  const float* depth;
+  const int32_t* rect4;
+  const int32_t* box_frame;
+  const FrameTab* tab;
+  const int32_t* list;
+  int32_t* counters;
+  int count_idx, cursor_idx;
+  int H, W;
+  uint32_t dmax_bits;
+  double quant;
+  double scale_depth;
+  lm3d_box_out* out;
+  float* order_stats;
+};
+
+struct Rect {
+  int x0, y0, x1, y1, w, h;
+};
+__device__ __forceinline__ Rect load_rect(const int32_t* rect4, int b, int H, int W) {
+  const int4 r = reinterpret_cast<const int4*>(rect4)[b];
+  const int xa = min(max(r.x, 0), W - 1), xb = min(max(r.z, 0), W - 1);
+  const int ya = min(max(r.y, 0), H - 1), yb = min(max(r.w, 0), H - 1);
+  Rect o;
+  o.x0 = min(xa, xb); o.x1 = max(xa, xb); o.y0 = min(ya, yb); o.y1 = max(ya, yb);
+  o.w = o.x1 - o.x0 + 1; o.h = o.y1 - o.y0 + 1;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. small boxes: one warp per box
+// ------------------------------------------------------------------------------------------
+// Lane layout inside a warp "slot" of 32 pixels: G lanes along the row, 32/G rows, so narrow
+// boxes (w < 32) still fill the warp.  A lane's column is fixed while it walks down the rows,
+// which makes the column part of the ray (a_k*u + c_k) loop-invariant.
+struct LaneMap {
+  int G, RP, lc, lr;
+};
+__device__ __forceinline__ LaneMap lane_map(int w, int lane) {
+  LaneMap m;
+  // pick the lane-group width with the fewest idle lanes (e.g. w = 40: 3 x 16 beats 2 x 32)
+  const int w8 = (w + 7) >> 3, w16 = (w + 15) >> 4, w32 = (w + 31) >> 5;
+  m.G = 32;
+  if (w16 * 16 < w32 * 32) m.G = 16;
+  if (w8 * 8 < ((m.G == 16) ? w16 * 16 : w32 * 32)) m.G = 8;
+  m.RP = 32 / m.G;
+  m.lc = lane & (m.G - 1);
+  m.lr = lane / m.G;
+  return m;
+}
+
+// Generic warp walk over the keys of a rect (used by the rare slow path only).
+template <typename Fn>
+__device__ __forceinline__ void warp_for_each_key(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                  uint32_t dmax_bits, int lane, Fn&& fn) {
+  const LaneMap lm = lane_map(rc.w, lane);
+  for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
+    const int cx = cx0 + lm.lc;
+    const bool col_ok = cx < rc.w;
+    const float* colp = fbase + (size_t)rc.y0 * W + rc.x0 + cx;
+    for (int ry0 = 0; ry0 < rc.h; ry0 += lm.RP) {
+      const int ry = ry0 + lm.lr;
+      const bool ok = col_ok && ry < rc.h;
+      const uint32_t bits = ok ? __float_as_uint(__ldg(colp + (size_t)ry * W)) : 0u;
+      fn(key_valid(bits, dmax_bits) ? bits : kKeyInvalid);
+    }
+  }
+}
+
+// Slow path: bisect the key range with counting passes over the rect until the window holds
+// <= kSmallCap keys, collect them, finish in shared memory.  Always terminates (<= 32 passes).
+__device__ __noinline__ void warp_select_global(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                uint32_t dmax_bits, int lane, uint32_t* cand, uint32_t wlo,
+                                                uint32_t whi, int below, int cnt, int r, bool two,
+                                                uint32_t& k0, uint32_t& k1) {
+  const uint32_t lt_mask = lanemask_lt();
+  while (true) {
+    if (cnt <= kSmallCap) {
+      int n = 0;
+      warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
+        const bool in = (key >= wlo) && (key <= whi);
+        const uint32_t bal = __ballot_sync(kFull, in);
+        if (in) cand[n + __popc(bal & lt_mask)] = key;
+        n += __popc(bal);
+      });
+      __syncwarp();
+      warp_select_smem(cand, n, r - below, two, lane, k0, k1);
+      return;
+    }
+    if (wlo == whi) {
+      k0 = k1 = wlo;
+      return;
+    }
+    const uint32_t mid = wlo + ((whi - wlo) >> 1);
+    int c_low = 0;
+    warp_for_each_key(fbase, W, rc, dmax_bits, lane,
+                      [&](uint32_t key) { c_low += (key >= wlo) && (key <= mid); });
+    c_low = warp_sum_i(c_low);
+    const int rr = r - below;
+    if (rr + (two ? 1 : 0) < c_low) {
+      whi = mid;
+      cnt = c_low;
+    } else if (rr >= c_low) {
+      wlo = mid + 1;
+      below += c_low;
+      cnt -= c_low;
+    } else {  // rank r is the largest key <= mid, rank r+1 the smallest key > mid
+      uint32_t bmax = 0u, amin = kKeyInvalid;
+      warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
+        if (key >= wlo && key <= mid) bmax = max(bmax, key);
+        if (key > mid && key <= whi) amin = min(amin, key);
+      });
+      k0 = warp_max_u(bmax);
+      k1 = warp_min_u(amin);
+      return;
+    }
+  }
+}
+
+template <int S_E>  // sample = 32*S_E keys
+__device__ __forceinline__ void small_sample_bracket(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                     int n_pix, uint32_t dmax_bits, double quant, int lane,
+                                                     uint32_t& lo, uint32_t& hi, bool& exact, int& sv_out,
+                                                     uint32_t (&s)[S_E]) {
+  constexpr int S = 32 * S_E;
+  exact = n_pix <= S;
+  int sv = 0;
+#pragma unroll
+  for (int e = 0; e < S_E; ++e) {
+    const int i = e * 32 + lane;
+    int idx;
+    bool ok = true;
+    if (exact) { idx = i; ok = i < n_pix; }
+    else idx = (int)(((long long)i * n_pix + (n_pix >> 1)) / S);
+    uint32_t bits = 0u;
+    if (ok) {
+      const int ry = idx / rc.w, cx = idx - ry * rc.w;
+      bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+    }
+    const bool v = key_valid(bits, dmax_bits);
+    s[e] = v ? bits : kKeyInvalid;
+    sv += v;
+  }
+  sv = warp_sum_i(sv);
+  warp_bitonic<S_E>(s, lane);
+  sv_out = sv;
+  if (exact) {  // the "sample" is the whole box: no bracket needed
+    lo = kKeyInvalid; hi = kKeyInvalid;
+    return;
+  }
+  int a, b;
+  bracket_ranks(sv, quant, kBracketZ, a, b);
+  const uint32_t sa = warp_sorted_at<S_E>(s, max(a, 0));
+  const uint32_t sb = warp_sorted_at<S_E>(s, min(max(b, 0), S - 1));
+  lo = (a < 0 || sv == 0) ? 1u : sa;
+  hi = (b >= sv || sv == 0) ? kKeyMaxValid : sb;
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32) lift_small_kernel(const LiftArgs A) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* cand = smem_u32 + wib * kSmallCap;
+  const uint32_t lt_mask = lanemask_lt();
+  const int n_items = A.counters[A.count_idx];
+  const int W = A.W;
+
+  while (true) {
+    int item0 = 0;
+    if (lane == 0) item0 = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);
+    item0 = __shfl_sync(kFull, item0, 0);
+    if (item0 >= n_items) break;
+    const int item1 = min(item0 + kSmallChunk, n_items);
+    for (int item = item0; item < item1; ++item) {
+      const int b = A.list[item];
+      const int f = A.box_frame[b];
+      const Rect rc = load_rect(A.rect4, b, A.H, W);
+      const int n_pix = rc.w * rc.h;
+      const float* __restrict__ fbase = A.depth + (size_t)f * A.H * W;
+      const float4* tp = reinterpret_cast<const float4*>(A.tab + f);
+      const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+      FrameTab tb;
+      tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
+      tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
+      tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+
+      // ---- sample -> bracket -------------------------------------------------------------
+      uint32_t lo, hi, ex0 = 0, ex1 = 0;
+      bool exact;
+      int sv;
+      if (n_pix <= 1536) {
+        uint32_t s[2];
+        small_sample_bracket<2>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, lane, lo, hi, exact, sv, s);
+        if (exact && sv > 0) {
+          int r; bool two; double g;
+          order_ranks(sv, A.quant, r, two, g);
+          ex0 = warp_sorted_at<2>(s, r);
+          ex1 = two ? warp_sorted_at<2>(s, r + 1) : ex0;
+        }
+      } else {
+        uint32_t s[8];
+        small_sample_bracket<8>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, lane, lo, hi, exact, sv, s);
+      }
+
+      // ---- fused pass: unproject + pose + reduce + bracket count/collect -----------------
+      const LaneMap lm = lane_map(rc.w, lane);
+      const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+      float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+      float s0_all = 0.f, su = 0.f, sv_acc = 0.f;
+      int n_valid = 0, c_lt = 0, ncand = 0;
+      const uint32_t span = hi - lo;
+      for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
+        const int cx = cx0 + lm.lc;
+        const bool col_ok = cx < rc.w;
+        const float uf = (float)(rc.x0 + cx);
+        const float ac0 = fmaf(tb.a[0], uf, tb.c[0]), ac1 = fmaf(tb.a[1], uf, tb.c[1]),
+                    ac2 = fmaf(tb.a[2], uf, tb.c[2]);
+        const float* colp = fbase + (size_t)rc.y0 * W + rc.x0 + cx;
+        float s0 = 0.f;
+        constexpr int U = 4;
+        for (int ry0 = 0; ry0 < rc.h; ry0 += lm.RP * U) {
+          uint32_t bits[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int ry = ry0 + j * lm.RP + lm.lr;
+            const bool ok = col_ok && ry < rc.h;
+            bits[j] = ok ? __float_as_uint(__ldg(colp + (size_t)ry * W)) : 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int ry = ry0 + j * lm.RP + lm.lr;
+            const bool valid = key_valid(bits[j], A.dmax_bits);
+            const float d = __uint_as_float(bits[j]);
+            const float vf = (float)(rc.y0 + ry);
+            if (valid) {
+              n_valid += 1;
+              s0 += d;
+              sv_acc = fmaf(vf - vc, d, sv_acc);
+              const float m0 = d * fmaf(tb.b[0], vf, ac0);
+              const float m1 = d * fmaf(tb.b[1], vf, ac1);
+              const float m2 = d * fmaf(tb.b[2], vf, ac2);
+              mn0 = fminf(mn0, m0); mx0 = fmaxf(mx0, m0);
+              mn1 = fminf(mn1, m1); mx1 = fmaxf(mx1, m1);
+              mn2 = fminf(mn2, m2); mx2 = fmaxf(mx2, m2);
+              c_lt += (bits[j] < lo);
+            }
+            const bool in = valid && ((bits[j] - lo) <= span);
+            const uint32_t bal = __ballot_sync(kFull, in);
+            if (in) {
+              const int pos = ncand + __popc(bal & lt_mask);
+              if (pos < kSmallCap) cand[pos] = bits[j];
+            }
+            ncand += __popc(bal);
+          }
+        }
+        su = fmaf(uf - uc, s0, su);
+        s0_all += s0;
+      }
+
+      // ---- warp reduction ----------------------------------------------------------------
+      BoxSums S;
+      S.n_valid = warp_sum_i(n_valid);
+      c_lt = warp_sum_i(c_lt);
+      S.s0 = warp_sum_d((double)s0_all);
+      S.su = warp_sum_d((double)su);
+      S.sv = warp_sum_d((double)sv_acc);
+      S.mn[0] = warp_min_f(mn0); S.mn[1] = warp_min_f(mn1); S.mn[2] = warp_min_f(mn2);
+      S.mx[0] = warp_max_f(mx0); S.mx[1] = warp_max_f(mx1); S.mx[2] = warp_max_f(mx2);
+      __syncwarp();
+
+      // ---- exact order statistics --------------------------------------------------------
+      uint32_t k0 = 0, k1 = 0;
+      double gamma = 0.0;
+      if (S.n_valid > 0) {
+        int r; bool two;
+        order_ranks(S.n_valid, A.quant, r, two, gamma);
+        if (exact) {
+          k0 = ex0; k1 = ex1;
+        } else {
+          const int c_in = ncand;
+          const int rhi = r + (two ? 1 : 0);
+          if (r >= c_lt && rhi < c_lt + c_in && c_in <= kSmallCap) {
+            warp_select_smem(cand, c_in, r - c_lt, two, lane, k0, k1);
+          } else {
+            uint32_t wlo = 1u, whi = kKeyMaxValid;
+            int below = 0, cnt = S.n_valid;
+            if (r >= c_lt && rhi < c_lt + c_in) { wlo = lo; whi = hi; below = c_lt; cnt = c_in; }
+            else if (rhi < c_lt) { whi = lo - 1u; cnt = c_lt; }
+            else if (r >= c_lt + c_in) { wlo = hi + 1u; below = c_lt + c_in; cnt = S.n_valid - below; }
+            warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, wlo, whi, below, cnt, r, two, k0, k1);
+          }
+        }
+      }
+      if (lane == 0)
+        write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
+                     tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. large boxes: one CTA per box
+// ------------------------------------------------------------------------------------------
+struct LargeShared {
+  double red_d[kLargeWarps][3];
+  float red_f[kLargeWarps][6];
+  int red_i[kLargeWarps][4];
+  uint32_t red_u[kLargeWarps][2];
+  int item;
+  int ncand;
+  int sv;
+  int bc_i[4];
+  uint32_t bc_u[2];
+};
+
+__device__ __forceinline__ int block_sum_i(int v, LargeShared& sh, int slot) {
+  v = warp_sum_i(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh.red_i[threadIdx.x >> 5][slot] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < kLargeWarps; ++w) t += sh.red_i[w][slot];
+  return t;
+}
+__device__ __forceinline__ void block_minmax_u(uint32_t& mn, uint32_t& mx, LargeShared& sh) {
+  mn = warp_min_u(mn);
+  mx = warp_max_u(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { sh.red_u[threadIdx.x >> 5][0] = mn; sh.red_u[threadIdx.x >> 5][1] = mx; }
+  __syncthreads();
+  uint32_t a = kKeyInvalid, b = 0u;
+#pragma unroll
+  for (int w = 0; w < kLargeWarps; ++w) { a = min(a, sh.red_u[w][0]); b = max(b, sh.red_u[w][1]); }
+  mn = a; mx = b;
+}
+
+// block bitonic sort of n (power of two, <= kSortCap) keys in shared memory
+__device__ void block_bitonic(uint32_t* buf, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n >> 1); t += kLargeThreads) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const bool up = ((i & size) == 0);
+        const uint32_t a = buf[i], b = buf[j];
+        if ((a > b) == up) { buf[i] = b; buf[j] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Key sources for the block-level window search
+struct RectSource {
+  const float* fbase; int W; Rect rc; uint32_t dmax_bits;
+  template <typename Fn> __device__ __forceinline__ void for_each(Fn&& fn) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int ry = warp; ry < rc.h; ry += kLargeWarps) {
+      const float* rowp = fbase + (size_t)(rc.y0 + ry) * W + rc.x0;
+      for (int cx0 = 0; cx0 < rc.w; cx0 += 32) {
+        const int cx = cx0 + lane;
+        const uint32_t bits = (cx < rc.w) ? __float_as_uint(__ldg(rowp + cx)) : 0u;
+        fn(key_valid(bits, dmax_bits) ? bits : kKeyInvalid);
+      }
+    }
+  }
+};
+struct SmemSource {
+  const uint32_t* buf; int m;
+  template <typename Fn> __device__ __forceinline__ void for_each(Fn&& fn) const {
+    const int m32 = (m + 31) & ~31;
+    for (int i = threadIdx.x; i < m32; i += kLargeThreads) fn(i < m ? buf[i] : kKeyInvalid);
+  }
+};
+
+// Find ranks r (and r+1) among the keys of `src` inside window [wlo,whi] (which is known to
+// hold `cnt` keys, with `below` keys before it): bisect until <= kSortCap keys, then sort.
+template <typename Src>
+__device__ void block_select_window(const Src& src, uint32_t wlo, uint32_t whi, int below, int cnt, int r, bool two,
+                                    uint32_t* sortbuf, LargeShared& sh, uint32_t& k0, uint32_t& k1) {
+  const uint32_t lt_mask = lanemask_lt();
+  while (true) {
+    if (cnt <= kSortCap) {
+      __syncthreads();
+      if (threadIdx.x == 0) sh.ncand = 0;
+      __syncthreads();
+      src.for_each([&](uint32_t key) {
+        const bool in = (key >= wlo) && (key <= whi);
+        const uint32_t bal = __ballot_sync(kFull, in);
+        int base = 0;
+        if (bal) {
+          if ((threadIdx.x & 31) == 0) base = atomicAdd(&sh.ncand, __popc(bal));
+          base = __shfl_sync(kFull, base, 0);
+          if (in) sortbuf[base + __popc(bal & lt_mask)] = key;
+        }
+      });
+      __syncthreads();
+      const int n = sh.ncand;
+      int np2 = 32;
+      while (np2 < n) np2 <<= 1;
+      for (int i = n + threadIdx.x; i < np2; i += kLargeThreads) sortbuf[i] = kKeyInvalid;
+      block_bitonic(sortbuf, np2);
+      k0 = sortbuf[r - below];
+      k1 = two ? sortbuf[r - below + 1] : k0;
+      __syncthreads();
+      return;
+    }
+    if (wlo == whi) { k0 = k1 = wlo; return; }
+    const uint32_t mid = wlo + ((whi - wlo) >> 1);
+    int c = 0;
+    src.for_each([&](uint32_t key) { c += (key >= wlo) && (key <= mid); });
+    const int c_low = block_sum_i(c, sh, 0);
+    const int rr = r - below;
+    if (rr + (two ? 1 : 0) < c_low) { whi = mid; cnt = c_low; }
+    else if (rr >= c_low) { wlo = mid + 1; below += c_low; cnt -= c_low; }
+    else {
+      uint32_t bmax = 0u, amin = kKeyInvalid;
+      src.for_each([&](uint32_t key) {
+        if (key >= wlo && key <= mid) bmax = max(bmax, key);
+        if (key > mid && key <= whi) amin = min(amin, key);
+      });
+      // block_minmax_u reduces (min of first, max of second): feed (amin, bmax)
+      block_minmax_u(amin, bmax, sh);
+      k0 = bmax; k1 = amin;
+      return;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLargeThreads) lift_large_kernel(const LiftArgs A) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  uint32_t* cand = smem_u32;                  // [kLargeCap]
+  uint32_t* sortbuf = smem_u32 + kLargeCap;   // [kSortCap]
+  __shared__ LargeShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = lanemask_lt();
+  const int n_items = A.counters[A.count_idx];
+  const int W = A.W;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) sh.item = atomicAdd(&A.counters[A.cursor_idx], 1);
+    __syncthreads();
+    const int item = sh.item;
+    if (item >= n_items) break;
+    const int b = A.list[item];
+    const int f = A.box_frame[b];
+    const Rect rc = load_rect(A.rect4, b, A.H, W);
+    const long long n_pix = (long long)rc.w * rc.h;
+    const float* __restrict__ fbase = A.depth + (size_t)f * A.H * W;
+    const float4* tp = reinterpret_cast<const float4*>(A.tab + f);
+    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+    FrameTab tb;
+    tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
+    tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
+    tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+
+    // ---- sample kSortCap pixels on a lattice, sort, bracket ------------------------------
+    int svl = 0;
+    for (int i = tid; i < kSortCap; i += kLargeThreads) {
+      const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / kSortCap;
+      const int ry = (int)(idx / rc.w), cx = (int)(idx - (long long)ry * rc.w);
+      const uint32_t bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+      const bool v = key_valid(bits, A.dmax_bits);
+      sortbuf[i] = v ? bits : kKeyInvalid;
+      svl += v;
+    }
+    const int sv = block_sum_i(svl, sh, 0);
+    block_bitonic(sortbuf, kSortCap);
+    uint32_t lo = 1u, hi = kKeyMaxValid;
+    if (sv > 0) {
+      int a, bb;
+      bracket_ranks(sv, A.quant, kBracketZ, a, bb);
+      if (a >= 0) lo = sortbuf[a];
+      if (bb < sv) hi = sortbuf[bb];
+    }
+    __syncthreads();
+    if (tid == 0) sh.ncand = 0;
+    __syncthreads();
+
+    // ---- fused pass ----------------------------------------------------------------------
+    const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+    float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+    float s0_all = 0.f, su = 0.f, sv_acc = 0.f;
+    int n_valid = 0, c_lt = 0;
+    const uint32_t span = hi - lo;
+    for (int cx0 = 0; cx0 < rc.w; cx0 += 32) {
+      const int cx = cx0 + lane;
+      const bool col_ok = cx < rc.w;
+      const float uf = (float)(rc.x0 + cx);
+      const float ac0 = fmaf(tb.a[0], uf, tb.c[0]), ac1 = fmaf(tb.a[1], uf, tb.c[1]),
+                  ac2 = fmaf(tb.a[2], uf, tb.c[2]);
+      const float* colp = fbase + (size_t)rc.y0 * W + rc.x0 + cx;
+      float s0 = 0.f;
+      constexpr int U = 4;
+      for (int ry0 = warp; ry0 < rc.h; ry0 += kLargeWarps * U) {
+        uint32_t bits[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int ry = ry0 + j * kLargeWarps;
+          const bool ok = col_ok && ry < rc.h;
+          bits[j] = ok ? __float_as_uint(__ldg(colp + (size_t)ry * W)) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int ry = ry0 + j * kLargeWarps;
+          const bool valid = key_valid(bits[j], A.dmax_bits);
+          const float d = __uint_as_float(bits[j]);
+          const float vf = (float)(rc.y0 + ry);
+          if (valid) {
+            n_valid += 1;
+            s0 += d;
+            sv_acc = fmaf(vf - vc, d, sv_acc);
+            const float m0 = d * fmaf(tb.b[0], vf, ac0);
+            const float m1 = d * fmaf(tb.b[1], vf, ac1);
+            const float m2 = d * fmaf(tb.b[2], vf, ac2);
+            mn0 = fminf(mn0, m0); mx0 = fmaxf(mx0, m0);
+            mn1 = fminf(mn1, m1); mx1 = fmaxf(mx1, m1);
+            mn2 = fminf(mn2, m2); mx2 = fmaxf(mx2, m2);
+            c_lt += (bits[j] < lo);
+          }
+          const bool in = valid && ((bits[j] - lo) <= span);
+          const uint32_t bal = __ballot_sync(kFull, in);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh.ncand, __popc(bal));
+            base = __shfl_sync(kFull, base, 0);
+            const int pos = base + __popc(bal & lt_mask);
+            if (in && pos < kLargeCap) cand[pos] = bits[j];
+          }
+        }
+      }
+      su = fmaf(uf - uc, s0, su);
+      s0_all += s0;
+    }
+
+    // ---- block reduction -----------------------------------------------------------------
+    {
+      const double d0 = warp_sum_d((double)s0_all), d1 = warp_sum_d((double)su), d2 = warp_sum_d((double)sv_acc);
+      const float f0 = warp_min_f(mn0), f1 = warp_min_f(mn1), f2 = warp_min_f(mn2);
+      const float f3 = warp_max_f(mx0), f4 = warp_max_f(mx1), f5 = warp_max_f(mx2);
+      const int i0 = warp_sum_i(n_valid), i1 = warp_sum_i(c_lt);
+      __syncthreads();
+      if (lane == 0) {
+        sh.red_d[warp][0] = d0; sh.red_d[warp][1] = d1; sh.red_d[warp][2] = d2;
+        sh.red_f[warp][0] = f0; sh.red_f[warp][1] = f1; sh.red_f[warp][2] = f2;
+        sh.red_f[warp][3] = f3; sh.red_f[warp][4] = f4; sh.red_f[warp][5] = f5;
+        sh.red_i[warp][0] = i0; sh.red_i[warp][1] = i1;
+      }
+      __syncthreads();
+    }
+    BoxSums S;
+    S.s0 = S.su = S.sv = 0.0;
+    S.n_valid = 0;
+    c_lt = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { S.mn[k] = INFINITY; S.mx[k] = -INFINITY; }
+    for (int w = 0; w < kLargeWarps; ++w) {
+      S.s0 += sh.red_d[w][0]; S.su += sh.red_d[w][1]; S.sv += sh.red_d[w][2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        S.mn[k] = fminf(S.mn[k], sh.red_f[w][k]);
+        S.mx[k] = fmaxf(S.mx[k], sh.red_f[w][3 + k]);
+      }
+      S.n_valid += sh.red_i[w][0];
+      c_lt += sh.red_i[w][1];
+    }
+    const int c_in = sh.ncand;
+    __syncthreads();
+
+    // ---- exact order statistics ----------------------------------------------------------
+    uint32_t k0 = 0, k1 = 0;
+    double gamma = 0.0;
+    if (S.n_valid > 0) {
+      int r; bool two;
+      order_ranks(S.n_valid, A.quant, r, two, gamma);
+      const int rhi = r + (two ? 1 : 0);
+      if (r >= c_lt && rhi < c_lt + c_in && c_in <= kLargeCap) {
+        SmemSource src{cand, c_in};
+        block_select_window(src, 0u, kKeyMaxValid, 0, c_in, r - c_lt, two, sortbuf, sh, k0, k1);
+      } else {
+        uint32_t wlo = 1u, whi = kKeyMaxValid;
+        int below = 0, cnt = S.n_valid;
+        if (r >= c_lt && rhi < c_lt + c_in) { wlo = lo; whi = hi; below = c_lt; cnt = c_in; }
+        else if (rhi < c_lt) { whi = lo - 1u; cnt = c_lt; }
+        else if (r >= c_lt + c_in) { wlo = hi + 1u; below = c_lt + c_in; cnt = S.n_valid - below; }
+        RectSource src{fbase, W, rc, A.dmax_bits};
+        block_select_window(src, wlo, whi, below, cnt, r, two, sortbuf, sh, k0, k1);
+      }
+    }
+    if (tid == 0)
+      write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr, tb,
+                   rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// full-frame world cloud (next-row #3: pose_processor.py:154-156, 262-271)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_cloud_kernel(const float* __restrict__ depth, int64_t F, int H, int W,
+                                                          const FrameTab* __restrict__ tab, uint32_t dmax_bits,
+                                                          float* __restrict__ xyz, int32_t* __restrict__ n_valid) {
+  // grid.y = frame; each thread handles 4 consecutive pixels (float4 load, 3 float4 stores)
+  const int64_t f = blockIdx.y;
+  const int hw = H * W;
+  const float* fb = depth + f * hw;
+  float* ob = xyz + f * (int64_t)hw * 3;
+  const float4* tp = reinterpret_cast<const float4*>(tab + f);
+  const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+  const float a0 = t0.x, a1 = t0.y, a2 = t0.z, b0 = t0.w, b1 = t1.x, b2 = t1.y, c0 = t1.z, c1 = t1.w, c2 = t2.x,
+              tx = t2.y, ty = t2.z, tz = t2.w;
+  const float qnan = __uint_as_float(0x7fc00000u);
+  int cnt = 0;
+  for (int p4 = blockIdx.x * blockDim.x + threadIdx.x; p4 * 4 < hw; p4 += gridDim.x * blockDim.x) {
+    const int p = p4 * 4;
+    float d[4];
+    if (p + 3 < hw && (hw & 3) == 0) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(fb + p));
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = (p + j < hw) ? __ldg(fb + p + j) : 0.f;
+    }
+    float o[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pp = p + j;
+      const int v = pp / W, u = pp - v * W;
+      const bool valid = key_valid(__float_as_uint(d[j]), dmax_bits) && pp < hw;
+      cnt += valid;
+      const float uf = (float)u, vf = (float)v;
+      o[3 * j + 0] = valid ? fmaf(d[j], fmaf(a0, uf, fmaf(b0, vf, c0)), tx) : qnan;
+      o[3 * j + 1] = valid ? fmaf(d[j], fmaf(a1, uf, fmaf(b1, vf, c1)), ty) : qnan;
+      o[3 * j + 2] = valid ? fmaf(d[j], fmaf(a2, uf, fmaf(b2, vf, c2)), tz) : qnan;
+    }
+    if (p + 3 < hw && (hw & 3) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(ob + (int64_t)p * 3);
+      o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+      o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+      o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+    } else {
+      for (int j = 0; j < 4 && p + j < hw; ++j)
+        for (int k = 0; k < 3; ++k) ob[(int64_t)(p + j) * 3 + k] = o[3 * j + k];
+    }
+  }
+  if (n_valid) {
+    cnt = warp_sum_i(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&n_valid[f], cnt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_launches{0};
+
+struct DeviceInfo {
+  int sms = 0;
+  bool ok = false;
+  bool attrs_set = false;
+};
+static DeviceInfo g_dev[64];
+
+static int device_info(DeviceInfo** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return LM3D_ERR_NO_DEVICE;
+  if (dev < 0 || dev >= 64) return LM3D_ERR_NO_DEVICE;
+  DeviceInfo& d = g_dev[dev];
+  if (!d.ok) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10)
+      return LM3D_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return LM3D_ERR_NO_DEVICE;
+    d.ok = true;
+  }
+  if (!d.attrs_set) {
+    e = cudaFuncSetAttribute(lift_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kSmallWarps * kSmallCap * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(lift_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (kLargeCap + kSortCap) * 4);
+    if (e != cudaSuccess) return (int)e;
+    d.attrs_set = true;
+  }
+  *out = &d;
+  return LM3D_OK;
+}
+
+static uint32_t dmax_to_bits(double max_depth_mm) {
+  if (!(max_depth_mm > 0.0)) return 0u;  // also NaN
+  float m = (max_depth_mm >= 3.4028234663852886e38) ? 3.4028234663852886e38f : (float)max_depth_mm;
+  // the float cast rounds to nearest; the ceiling must not admit d > max_depth_mm
+  if ((double)m > max_depth_mm) m = nextafterf(m, 0.0f);
+  if (!(m > 0.0f)) return 0u;
+  uint32_t b;
+  memcpy(&b, &m, 4);
+  return b;
+}
+
+}  // namespace lm3d
+
+using namespace lm3d;
+
+extern "C" {
+
+int lm3d_version(void) { return LM3D_VERSION; }
+
+const char* lm3d_status_string(int s) {
+  switch (s) {
+    case LM3D_OK: return "ok";
+    case LM3D_ERR_BAD_ARG: return "bad argument";
+    case LM3D_ERR_WORKSPACE: return "workspace too small";
+    case LM3D_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
+    case LM3D_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case LM3D_ERR_TOO_LARGE: return "problem exceeds int32 indexing limits";
+    default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown lm3d status";
+  }
+}
+
+int64_t lm3d_kernel_launches(void) { return g_launches.load(); }
+
+size_t lm3d_workspace_bytes(int64_t F, int64_t B) {
+  if (F < 0 || B < 0) return 0;
+  return workspace_layout(F, B, nullptr, nullptr);
+}
+
+int lm3d_scale_boxes(const double* boxes_xyxy, const double* image_wh, const int64_t* frame_off, int64_t F,
+                     int64_t B, int32_t depth_w, int32_t depth_h, int32_t* rect4_out, void* stream) {
+  if (B < 0 || F < 0 || depth_w < 1 || depth_h < 1) return LM3D_ERR_BAD_ARG;
+  if (B == 0) return LM3D_OK;
+  if (!boxes_xyxy || !image_wh || !frame_off || !rect4_out || F < 1) return LM3D_ERR_BAD_ARG;
+  if (((uintptr_t)rect4_out & 15) != 0) return LM3D_ERR_ALIGNMENT;
+  if (B > INT32_MAX) return LM3D_ERR_TOO_LARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  scale_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(boxes_xyxy, image_wh, frame_off, F, B, depth_w,
+                                                                depth_h, rect4_out);
+  g_launches += 1;
+  return (int)cudaGetLastError();
+}
+
+int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7, const double* intr4,
+                    const int32_t* rect4, const int64_t* frame_off, int64_t B, double scale_depth,
+                    double max_depth_mm, double q_percent, lm3d_box_out* out, float* order_stats, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (F < 0 || B < 0 || H < 1 || W < 1) return LM3D_ERR_BAD_ARG;
+  if (!(q_percent >= 0.0 && q_percent <= 100.0)) return LM3D_ERR_BAD_ARG;
+  if (!(scale_depth > 0.0)) return LM3D_ERR_BAD_ARG;
+  if (B == 0) return LM3D_OK;
+  if (F < 1 || !depth || !pose7 || !intr4 || !rect4 || !frame_off || !out || !workspace) return LM3D_ERR_BAD_ARG;
+  if ((int64_t)H * W > (int64_t)1 << 30 || B > INT32_MAX - 64 || F > INT32_MAX) return LM3D_ERR_TOO_LARGE;
+  if ((((uintptr_t)depth | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)rect4) & 15) != 0)
+    return LM3D_ERR_ALIGNMENT;
+  if (workspace_bytes < lm3d_workspace_bytes(F, B)) return LM3D_ERR_WORKSPACE;
+  DeviceInfo* dev = nullptr;
+  int rc = device_info(&dev);
+  if (rc != LM3D_OK) return rc;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws;
+  workspace_layout(F, B, (char*)workspace, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.counters, 0, 64, st);
+  if (e != cudaSuccess) return (int)e;
+
+  prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, ws.tab);
+  prep_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, frame_off, F, B, H, W, ws.box_frame,
+                                                               ws.small_list, ws.large_list, ws.counters);
+  LiftArgs A;
+  A.depth = depth; A.rect4 = rect4; A.box_frame = ws.box_frame; A.tab = ws.tab;
+  A.counters = ws.counters; A.H = H; A.W = W;
+  A.dmax_bits = dmax_to_bits(max_depth_mm);
+  A.quant = q_percent / 100.0;
+  A.scale_depth = scale_depth;
+  A.out = out; A.order_stats = order_stats;
+
+  // persistent grids: a multiple of the SM count, capped by the amount of work
+  {
+    A.list = ws.small_list; A.count_idx = 0; A.cursor_idx = 2;
+    const int64_t want = (B + (int64_t)kSmallWarps * kSmallChunk - 1) / ((int64_t)kSmallWarps * kSmallChunk);
+    const int ctas_per_sm = 3;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * ctas_per_sm));
+    lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
+  }
+  {
+    A.list = ws.large_list; A.count_idx = 1; A.cursor_idx = 3;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)dev->sms * 2));
+    lift_large_kernel<<<grid, kLargeThreads, (kLargeCap + kSortCap) * 4, st>>>(A);
+  }
+  g_launches += 4;
+  return (int)cudaGetLastError();
+}
+
+int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
+                          const double* intr4, double scale_depth, double max_depth_mm, float* xyz,
+                          int32_t* n_valid, void* stream) {
+  if (F < 0 || H < 1 || W < 1 || !(scale_depth > 0.0)) return LM3D_ERR_BAD_ARG;
+  if (F == 0) return LM3D_OK;
+  if (!depth || !pose7 || !intr4 || !xyz) return LM3D_ERR_BAD_ARG;
+  if ((int64_t)H * W > (int64_t)1 << 30 || F > 65535) return LM3D_ERR_TOO_LARGE;
+  if ((((uintptr_t)depth | (uintptr_t)xyz) & 15) != 0) return LM3D_ERR_ALIGNMENT;
+  DeviceInfo* dev = nullptr;
+  int rc = device_info(&dev);
+  if (rc != LM3D_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameTab* tab = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&tab, (size_t)F * sizeof(FrameTab), st);
+  if (e != cudaSuccess) return (int)e;
+  if (n_valid) {
+    e = cudaMemsetAsync(n_valid, 0, (size_t)F * 4, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, tab);
+  const int hw4 = (H * W + 3) / 4;
+  const unsigned gx = (unsigned)std::max(1, std::min((hw4 + 255) / 256, dev->sms * 8));
+  frame_cloud_kernel<<<dim3(gx, (unsigned)F), 256, 0, st>>>(depth, F, H, W, tab, dmax_to_bits(max_depth_mm), xyz,
+                                                            n_valid);
+  g_launches += 2;
+  e = cudaGetLastError();
+  cudaFreeAsync(tab, st);
+  return (int)e;
+}
+
+int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
+                         const double* intr4, const double* boxes_xyxy, const double* image_wh,
+                         const int64_t* frame_off, int64_t B, double scale_depth, double max_depth_mm,
+                         double q_percent, lm3d_box_out* out, int device) {
+  if (F < 0 || B < 0 || H < 1 || W < 1) return LM3D_ERR_BAD_ARG;
+  if (!(q_percent >= 0.0 && q_percent <= 100.0) || !(scale_depth > 0.0)) return LM3D_ERR_BAD_ARG;
+  if (B == 0) return LM3D_OK;
+  if (F < 1 || !depth || !pose7 || !intr4 || !boxes_xyxy || !image_wh || !frame_off || !out) return LM3D_ERR_BAD_ARG;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return LM3D_ERR_NO_DEVICE;
+
+  // frame chunks sized to ~64 MB of depth, double buffered: copy(k+1) overlaps lift(k)
+  const size_t frame_bytes = (size_t)H * W * 4;
+  int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)64 << 20) / frame_bytes);
+  if (chunk > F) chunk = F;
+  int64_t max_boxes = 0;
+  for (int64_t f0 = 0; f0 < F; f0 += chunk) {
+    const int64_t f1 = std::min(F, f0 + chunk);
+    max_boxes = std::max(max_boxes, frame_off[f1] - frame_off[f0]);
+  }
+  if (frame_off[0] != 0 || frame_off[F] != B) return LM3D_ERR_BAD_ARG;
+
+  struct Slot {
+    cudaStream_t st = nullptr;
+    float* depth = nullptr;
+    double *pose = nullptr, *intr = nullptr, *boxes = nullptr, *wh = nullptr;
+    int64_t* off = nullptr;
+    int32_t* rect = nullptr;
+    lm3d_box_out* out = nullptr;
+    void* ws = nullptr;
+    int64_t* off_host = nullptr;
+  } slot[2];
+  const size_t ws_bytes = lm3d_workspace_bytes(chunk, std::max<int64_t>(max_boxes, 1));
+  int rc = LM3D_OK;
+  auto ck = [&](cudaError_t err) { if (err != cudaSuccess && rc == LM3D_OK) rc = (int)err; return err == cudaSuccess; };
+  for (int s = 0; s < 2 && rc == LM3D_OK; ++s) {
+    Slot& S = slot[s];
+    ck(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    ck(cudaMalloc((void**)&S.depth, (size_t)chunk * frame_bytes));
+    ck(cudaMalloc((void**)&S.pose, (size_t)chunk * 7 * 8));
+    ck(cudaMalloc((void**)&S.intr, (size_t)chunk * 4 * 8));
+    ck(cudaMalloc((void**)&S.wh, (size_t)chunk * 2 * 8));
+    ck(cudaMalloc((void**)&S.off, (size_t)(chunk + 1) * 8));
+    ck(cudaMalloc((void**)&S.boxes, (size_t)std::max<int64_t>(max_boxes, 1) * 4 * 8));
+    ck(cudaMalloc((void**)&S.rect, (size_t)std::max<int64_t>(max_boxes, 1) * 16));
+    ck(cudaMalloc((void**)&S.out, (size_t)std::max<int64_t>(max_boxes, 1) * sizeof(lm3d_box_out)));
+    ck(cudaMalloc(&S.ws, ws_bytes));
+    ck(cudaMallocHost((void**)&S.off_host, (size_t)(chunk + 1) * 8));
+  }
+  int k = 0;
+  for (int64_t f0 = 0; f0 < F && rc == LM3D_OK; f0 += chunk, k ^= 1) {
+    Slot& S = slot[k];
+    const int64_t f1 = std::min(F, f0 + chunk), nf = f1 - f0;
+    const int64_t b0 = frame_off[f0], nb = frame_off[f1] - b0;
+    ck(cudaStreamSynchronize(S.st));  // slot free again (its previous D2H finished)
+    for (int64_t i = 0; i <= nf; ++i) S.off_host[i] = frame_off[f0 + i] - b0;
+    ck(cudaMemcpyAsync(S.depth, depth + (size_t)f0 * H * W, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, S.st));
+    ck(cudaMemcpyAsync(S.pose, pose7 + f0 * 7, (size_t)nf * 56, cudaMemcpyHostToDevice, S.st));
+    ck(cudaMemcpyAsync(S.intr, intr4 + f0 * 4, (size_t)nf * 32, cudaMemcpyHostToDevice, S.st));
+    ck(cudaMemcpyAsync(S.wh, image_wh + f0 * 2, (size_t)nf * 16, cudaMemcpyHostToDevice, S.st));
+    ck(cudaMemcpyAsync(S.off, S.off_host, (size_t)(nf + 1) * 8, cudaMemcpyHostToDevice, S.st));
+    if (nb > 0) {
+      ck(cudaMemcpyAsync(S.boxes, boxes_xyxy + b0 * 4, (size_t)nb * 32, cudaMemcpyHostToDevice, S.st));
+      if (rc == LM3D_OK) rc = lm3d_scale_boxes(S.boxes, S.wh, S.off, nf, nb, W, H, S.rect, S.st);
+      if (rc == LM3D_OK)
+        rc = lm3d_lift_boxes(S.depth, nf, H, W, S.pose, S.intr, S.rect, S.off, nb, scale_depth, max_depth_mm,
+                             q_percent, S.out, nullptr, S.ws, ws_bytes, S.st);
+      ck(cudaMemcpyAsync(out + b0, S.out, (size_t)nb * sizeof(lm3d_box_out), cudaMemcpyDeviceToHost, S.st));
+    }
+  }
+  for (int s = 0; s < 2; ++s) {
+    Slot& S = slot[s];
+    if (S.st) ck(cudaStreamSynchronize(S.st));
+    cudaFree(S.depth); cudaFree(S.pose); cudaFree(S.intr); cudaFree(S.wh); cudaFree(S.off);
+    cudaFree(S.boxes); cudaFree(S.rect); cudaFree(S.out); cudaFree(S.ws);
+    if (S.off_host) cudaFreeHost(S.off_host);
+    if (S.st) cudaStreamDestroy(S.st);
+  }
+  return rc;
+}
+
+}  // extern "C"

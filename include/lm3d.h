@@ -1,0 +1,115 @@
+/* lm3d.h -- C ABI of the B200-native 2D-box -> 3D lift (liblm3d.so).
+ *
+ * The reference (ben-sanati/3d-localisation-and-mapping) has no FFI / plugin interface for
+ * this path: the boundary is the Python method ProcessPose.get_global_coordinates()
+ * (src/mapper/pose_processor.py:88-122).  These entry points are what a binding for that
+ * method calls; each one cites the reference code it replaces.  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - unless a function name ends in _host, every pointer is a DEVICE pointer owned by the
+ *     caller, the library allocates nothing persistent, enqueues on the given cudaStream_t
+ *     (passed as void*; NULL = legacy default stream) and never synchronises;
+ *   - re-entrant across streams/threads as long as each call has its own workspace;
+ *   - returns LM3D_OK (0), a negative lm3d_status, or a positive cudaError_t; never throws.
+ */
+#ifndef LM3D_H_
+#define LM3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM3D_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  LM3D_OK = 0,
+  LM3D_ERR_BAD_ARG = -1,      /* null pointer, negative size, q outside [0,100], H/W < 1 */
+  LM3D_ERR_WORKSPACE = -2,    /* workspace_bytes < lm3d_workspace_bytes(F, B)           */
+  LM3D_ERR_ALIGNMENT = -3,    /* depth / out / workspace not 16-byte aligned            */
+  LM3D_ERR_NO_DEVICE = -4,    /* no CUDA device / wrong architecture (needs sm_100)     */
+  LM3D_ERR_TOO_LARGE = -5     /* H*W or B exceeds int32 indexing limits                 */
+} lm3d_status;
+
+/* One record per box, 96 bytes.  Replaces the per-box result assembled at
+ * pose_processor.py:184-208 (corners = the reference's row, the rest = north_star extras).
+ *   corners   world XYZ of the rect corners TL,BL,BR,TR (order: detector.py:202), each
+ *             lifted with the box's percentile depth (pose_processor.py:183-201)
+ *   centroid  mean world XYZ of the valid pixels in the rect
+ *   aabb_*    per-axis world min / max over the valid pixels
+ *   z_q       percentile depth in metres (d_q / scale_depth)
+ *   n_valid   pixels with finite 0 < d <= max_depth_mm;  n_pix = rect area
+ * n_valid == 0  =>  every float field is NaN. */
+typedef struct {
+  float corners[4][3];
+  float centroid[3];
+  float aabb_min[3];
+  float aabb_max[3];
+  float z_q;
+  int32_t n_valid;
+  int32_t n_pix;
+} lm3d_box_out;
+
+int lm3d_version(void);
+const char* lm3d_status_string(int status);
+
+/* Scratch the lift needs for F frames / B boxes (frame table, box->frame map, work lists). */
+size_t lm3d_workspace_bytes(int64_t F, int64_t B);
+
+/* Detector boxes (RGB pixels) -> inclusive, clamped integer pixel rects at depth resolution.
+ * Replaces Transforms.scale_bounding_box + bbox_to_3d + the int() truncation
+ * (pose_processor.py:174-181, :186-187).  fp64: x*dw/iw, y*dh/ih, trunc toward zero, clamp
+ * to [0,dw-1]/[0,dh-1], order so x0<=x1, y0<=y1.
+ *   boxes_xyxy [B,4] f64 (x1,y1,x2,y2)     image_wh [F,2] f64 (image_width,image_height)
+ *   frame_off  [F+1] i64 CSR offsets        rect4_out [B,4] i32 (x0,y0,x1,y1)            */
+int lm3d_scale_boxes(const double* boxes_xyxy, const double* image_wh, const int64_t* frame_off,
+                     int64_t F, int64_t B, int32_t depth_w, int32_t depth_h, int32_t* rect4_out,
+                     void* stream);
+
+/* The hot path: replaces the per-frame / per-box body of ProcessPose._3d_processing
+ * (pose_processor.py:124-240) and _transform_to_global (:242-260) for a whole sequence.
+ *   depth       [F,H,W] f32 millimetres, row-major (dataset.py:68-81), 16-byte aligned
+ *   pose7       [F,7] f64  tx ty tz qx qy qz qw  (database_query.py:22-24; row i = frame i)
+ *   intr4       [F,4] f64  fx fy cx cy ALREADY at depth resolution (pose_processor.py:133-137)
+ *   rect4       [B,4] i32  inclusive pixel rects (lm3d_scale_boxes output); re-clamped here
+ *   frame_off   [F+1] i64  CSR: boxes of frame f are [frame_off[f], frame_off[f+1])
+ *   scale_depth            depth units per metre (pose_processor.py:49, default 1000)
+ *   max_depth_mm           validity ceiling, +inf = none
+ *   q_percent              percentile in [0,100] (50 = the reference's median, :183)
+ *   out         [B] lm3d_box_out, 16-byte aligned
+ *   order_stats [B,2] f32 or NULL: the two raw order statistics (mm) the percentile used
+ *   workspace   >= lm3d_workspace_bytes(F,B) bytes, 16-byte aligned                     */
+int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
+                    const double* intr4, const int32_t* rect4, const int64_t* frame_off, int64_t B,
+                    double scale_depth, double max_depth_mm, double q_percent, lm3d_box_out* out,
+                    float* order_stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Full-frame world point cloud: replaces Visualiser.gen_rgbd + gen_point_cloud
+ * (pose_processor.py:154-156, 262-271; Open3D unprojection + extrinsic) for F frames.
+ *   xyz [F,H,W,3] f32 world coordinates, NaN where the depth pixel is invalid
+ *   n_valid [F] i32 (may be NULL)                                                        */
+int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
+                          const double* intr4, double scale_depth, double max_depth_mm, float* xyz,
+                          int32_t* n_valid, void* stream);
+
+/* Host-buffer convenience for bindings without a device allocator (the e2e path): copies the
+ * sequence to the device in frame chunks on two streams (copy overlapped with compute), runs
+ * lm3d_scale_boxes + lm3d_lift_boxes, copies the records back, synchronises.  All pointers are
+ * HOST pointers (pinned memory makes the copies asynchronous).  boxes_xyxy are RGB-pixel
+ * detector boxes; intr4 is at depth resolution.  device = CUDA ordinal.                  */
+int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
+                         const double* intr4, const double* boxes_xyxy, const double* image_wh,
+                         const int64_t* frame_off, int64_t B, double scale_depth, double max_depth_mm,
+                         double q_percent, lm3d_box_out* out, int device);
+
+/* Launch counter: number of lm3d kernels enqueued by this process so far (bench evidence). */
+int64_t lm3d_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM3D_H_ */
