@@ -828,6 +828,15 @@ __global__ void __launch_bounds__(256) frame_cloud_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------
 static std::atomic<int64_t> g_launches{0};
 
+// Optional per-kernel timing of lm3d_lift_boxes (bench.py's roofline leg): when enabled, five
+// events bracket the four kernels on the caller's stream.  Not thread-safe; off by default.
+static bool g_profile = false;
+static cudaEvent_t g_prof_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static bool g_prof_valid = false;
+static inline void prof_mark(int i, cudaStream_t st) {
+  if (g_profile) cudaEventRecord(g_prof_ev[i], st);
+}
+
 struct DeviceInfo {
   int sms = 0;
   bool ok = false;
@@ -894,6 +903,29 @@ const char* lm3d_status_string(int s) {
 
 int64_t lm3d_kernel_launches(void) { return g_launches.load(); }
 
+int lm3d_profile_enable(int on) {
+  if (on && !g_prof_ev[0]) {
+    for (int i = 0; i < 5; ++i) {
+      cudaError_t e = cudaEventCreate(&g_prof_ev[i]);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  g_profile = on != 0;
+  g_prof_valid = false;
+  return LM3D_OK;
+}
+
+int lm3d_profile_read(float* ms4) {
+  if (!ms4 || !g_prof_valid) return LM3D_ERR_BAD_ARG;
+  cudaError_t e = cudaEventSynchronize(g_prof_ev[4]);
+  if (e != cudaSuccess) return (int)e;
+  for (int i = 0; i < 4; ++i) {
+    e = cudaEventElapsedTime(&ms4[i], g_prof_ev[i], g_prof_ev[i + 1]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return LM3D_OK;
+}
+
 size_t lm3d_workspace_bytes(int64_t F, int64_t B) {
   if (F < 0 || B < 0) return 0;
   return workspace_layout(F, B, nullptr, nullptr);
@@ -936,9 +968,12 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   cudaError_t e = cudaMemsetAsync(ws.counters, 0, 64, st);
   if (e != cudaSuccess) return (int)e;
 
+  prof_mark(0, st);
   prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, ws.tab);
+  prof_mark(1, st);
   prep_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, frame_off, F, B, H, W, ws.box_frame,
                                                                ws.small_list, ws.large_list, ws.counters);
+  prof_mark(2, st);
   LiftArgs A;
   A.depth = depth; A.rect4 = rect4; A.box_frame = ws.box_frame; A.tab = ws.tab;
   A.counters = ws.counters; A.H = H; A.W = W;
@@ -955,11 +990,14 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * ctas_per_sm));
     lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
   }
+  prof_mark(3, st);
   {
     A.list = ws.large_list; A.count_idx = 1; A.cursor_idx = 3;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)dev->sms * 2));
     lift_large_kernel<<<grid, kLargeThreads, (kLargeCap + kSortCap) * 4, st>>>(A);
   }
+  prof_mark(4, st);
+  g_prof_valid = g_profile;
   g_launches += 4;
   return (int)cudaGetLastError();
 }

@@ -25,6 +25,8 @@ SYMBOLS = (
     "lm3d_lift_frame_cloud",
     "lm3d_lift_boxes_host",
     "lm3d_kernel_launches",
+    "lm3d_profile_enable",
+    "lm3d_profile_read",
 )
 
 
@@ -72,6 +74,10 @@ def load():
     lib.lm3d_lift_boxes_host.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, C.c_int]
     lib.lm3d_kernel_launches.restype = i64
     lib.lm3d_kernel_launches.argtypes = []
+    lib.lm3d_profile_enable.restype = C.c_int
+    lib.lm3d_profile_enable.argtypes = [C.c_int]
+    lib.lm3d_profile_read.restype = C.c_int
+    lib.lm3d_profile_read.argtypes = [vp]
     _lib = lib
     return lib
 

@@ -109,6 +109,13 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
 /* Launch counter: number of lm3d kernels enqueued by this process so far (bench evidence). */
 int64_t lm3d_kernel_launches(void);
 
+/* Measurement hooks (bench.py's roofline leg; not part of the data path, not thread-safe).
+ * While enabled, lm3d_lift_boxes brackets its four kernels with CUDA events on the caller's
+ * stream; lm3d_profile_read waits for the last call and returns the four durations in ms:
+ * [0] frame table, [1] box prep, [2] warp-per-box lift, [3] CTA-per-box lift. */
+int lm3d_profile_enable(int on);
+int lm3d_profile_read(float* ms4);
+
 #ifdef __cplusplus
 }
 #endif
