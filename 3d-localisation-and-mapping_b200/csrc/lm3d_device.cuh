@@ -116,95 +116,156 @@ __device__ __forceinline__ void bracket_ranks(int sv, double quant, float z, int
 }
 
 // ---------------------------------------------------------------------------------------
-// Exact selection of ranks r (and r+1 if two) among m keys in shared memory, one warp.
-// Rounds of: 32-key strided sample -> sort -> bracket -> count pass -> in-place compaction.
-// Falls back to bisecting the numeric key range when a round cannot shrink the set (ties).
-// buf is clobbered.
+// sm_100a packed fp32 (FFMA2 / FMUL2 / FADD2) and 3-input min/max (FMNMX3)
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void warp_select_smem(uint32_t* buf, int m, int r, bool two, int lane,
-                                              uint32_t& k0, uint32_t& k1) {
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// NaN operands are ignored (IEEE minNum/maxNum), which is how invalid pixels drop out
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact selection of ranks r (and r+1 if two) among m keys in shared memory, one warp.
+//
+// buf holds every key of the box inside the key window [wlo,whi] (plus optional 0xffffffff
+// padding, which sorts last); `below` keys of the box are smaller than the window.
+// Rounds: 32-key strided sample -> sort -> bracket -> ONE pass that counts keys below the
+// bracket and compacts the bracket in place.  If the target rank falls outside a bracket
+// the discarded keys are gone, so the routine returns false with the (now smaller) window
+// that holds the target and the caller re-reads those keys from global memory.  Rounds that
+// cannot shrink the set (heavy ties) bisect the numeric key range instead (count first).
+// ---------------------------------------------------------------------------------------
+struct SelWindow {
+  uint32_t wlo, whi;  // inclusive key window known to contain ranks r (and r+1)
+  int below;          // keys of the box smaller than wlo
+  int cnt;            // keys of the box inside the window (upper bound is fine)
+  bool straddle;      // set on failure: rank r is the largest key < split, r+1 the smallest >= split
+  uint32_t split;
+};
+
+__device__ __noinline__ bool warp_select_smem(uint32_t* buf, int m, int n_pad, int r, bool two, int lane,
+                                              SelWindow& win, uint32_t& k0, uint32_t& k1) {
+  // r is relative to the window (rank r of the box == rank r - win.below here)
   const uint32_t lt_mask = lanemask_lt();
   bool bisect = false;
   while (m > 64) {
-    uint32_t lo, hi;
-    if (!bisect) {
-      const int idx = (int)(((long long)lane * m + (m >> 1)) >> 5);
-      uint32_t s[1] = {buf[idx]};
-      warp_bitonic<1>(s, lane);
-      const float p = ((float)r + 0.5f) * (32.0f / (float)m);
-      const float fr = fminf(fmaxf(p * (1.0f / 32.0f), 0.0f), 1.0f);
-      const float delta = 2.5f * sqrtf(32.0f * fr * (1.0f - fr)) + 1.5f;
-      const int a = (int)floorf(p - delta);
-      const int b = (int)ceilf(p + 1.0f + delta);
-      const uint32_t sa = __shfl_sync(kFull, s[0], max(a, 0));
-      const uint32_t sb = __shfl_sync(kFull, s[0], min(b, 31));
-      lo = (a < 0) ? 0u : sa;
-      hi = (b > 31) ? kKeyInvalid : sb;
-    } else {
+    if (bisect) {
+      // count first: the half that does not hold the target must not be destroyed blindly
       uint32_t mn = kKeyInvalid, mx = 0u;
       for (int i = lane; i < m; i += 32) {
         const uint32_t k = buf[i];
-        mn = min(mn, k);
-        mx = max(mx, k);
+        if (k != kKeyInvalid) { mn = min(mn, k); mx = max(mx, k); }
       }
       mn = warp_min_u(mn);
       mx = warp_max_u(mx);
-      if (mn == mx) {
-        k0 = k1 = mn;
-        return;
+      if (mn >= mx) { k0 = k1 = mn; return true; }
+      const uint32_t mid = mn + ((mx - mn) >> 1);
+      int c_low = 0;
+      for (int i = lane; i < m; i += 32) c_low += (buf[i] <= mid);
+      c_low = warp_sum_i(c_low);
+      if (two && r + 1 == c_low) {  // r = largest key <= mid, r+1 = smallest key > mid
+        uint32_t bmax = 0u, amin = kKeyInvalid;
+        for (int i = lane; i < m; i += 32) {
+          const uint32_t k = buf[i];
+          if (k <= mid) bmax = max(bmax, k); else amin = min(amin, k);
+        }
+        k0 = warp_max_u(bmax);
+        k1 = warp_min_u(amin);
+        return true;
       }
-      lo = 0u;
-      hi = mn + ((mx - mn) >> 1);
+      const bool low = r < c_low;
+      int wpos = 0;
+      for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const uint32_t k = (i < m) ? buf[i] : kKeyInvalid;
+        const bool keep = (i < m) && ((k <= mid) == low) && (k != kKeyInvalid);
+        const uint32_t bal = __ballot_sync(kFull, keep);
+        if (keep) buf[wpos + __popc(bal & lt_mask)] = k;
+        wpos += __popc(bal);
+        __syncwarp();
+      }
+      if (low) { win.whi = mid; }
+      else { win.wlo = mid + 1; win.below += c_low; r -= c_low; }
+      m = wpos; n_pad = 0; win.cnt = m;
       bisect = false;
-    }
-    // count pass
-    int c_lt = 0, c_in = 0;
-    for (int i = lane; i < m; i += 32) {
-      const uint32_t k = buf[i];
-      c_lt += (k < lo);
-      c_in += (k >= lo && k <= hi);
-    }
-    c_lt = warp_sum_i(c_lt);
-    c_in = warp_sum_i(c_in);
-    // straddles: rank r is the largest key of the lower part, r+1 the smallest of the upper
-    if (two && (r + 1 == c_lt || r + 1 == c_lt + c_in)) {
-      const bool at_lo = (r + 1 == c_lt);
-      uint32_t below_max = 0u, above_min = kKeyInvalid;
-      for (int i = lane; i < m; i += 32) {
-        const uint32_t k = buf[i];
-        const bool lower = at_lo ? (k < lo) : (k <= hi);
-        if (lower) below_max = max(below_max, k);
-        else above_min = min(above_min, k);
-      }
-      k0 = warp_max_u(below_max);
-      k1 = warp_min_u(above_min);
-      return;
-    }
-    int part, m_new, r_new;  // 0 = LT, 1 = IN, 2 = GT
-    if (r < c_lt) { part = 0; m_new = c_lt; r_new = r; }
-    else if (r < c_lt + c_in) { part = 1; m_new = c_in; r_new = r - c_lt; }
-    else { part = 2; m_new = m - c_lt - c_in; r_new = r - c_lt - c_in; }
-    if (m_new == m) {  // nothing discarded: sample bracket useless (heavy ties) -> bisect values
-      bisect = true;
       continue;
     }
-    // in-place compaction of the chosen part (write index never passes the read index)
-    int wpos = 0;
+    // ---- sample 32 -> bracket ----
+    const int idx = (int)(((long long)lane * m + (m >> 1)) >> 5);
+    uint32_t s[1] = {buf[idx]};
+    warp_bitonic<1>(s, lane);
+    const int m_real = m - n_pad;
+    const float p = ((float)r + 0.5f) * (32.0f / (float)m);
+    const float fr = fminf(fmaxf(p * (1.0f / 32.0f), 0.0f), 1.0f);
+    const float delta = 2.5f * sqrtf(32.0f * fr * (1.0f - fr)) + 1.5f;
+    const int a = (int)floorf(p - delta);
+    const int b = (int)ceilf(p + 1.0f + delta);
+    const uint32_t sa = __shfl_sync(kFull, s[0], max(a, 0));
+    const uint32_t sb = __shfl_sync(kFull, s[0], min(b, 31));
+    // clamp into the window: the sample may contain 0xffffffff padding (sorts last)
+    const uint32_t hi = (b > 31) ? win.whi : max(min(sb, win.whi), win.wlo);
+    const uint32_t lo = (a < 0) ? win.wlo : min(max(sa, win.wlo), hi);
+    const uint32_t span = hi - lo;
+    // ---- one pass: count below, compact bracket in place ----
+    int c_lt = 0, wpos = 0;
     for (int base = 0; base < m; base += 32) {
       const int i = base + lane;
-      const uint32_t k = (i < m) ? buf[i] : 0u;
-      bool keep = (i < m);
-      if (part == 0) keep = keep && (k < lo);
-      else if (part == 1) keep = keep && (k >= lo && k <= hi);
-      else keep = keep && (k > hi);
-      const uint32_t bal = __ballot_sync(kFull, keep);
-      __syncwarp();
-      if (keep) buf[wpos + __popc(bal & lt_mask)] = k;
+      const uint32_t k = (i < m) ? buf[i] : kKeyInvalid;
+      c_lt += (k < lo);
+      const bool in = (k - lo) <= span;
+      const uint32_t bal = __ballot_sync(kFull, in);
+      if (in) buf[wpos + __popc(bal & lt_mask)] = k;
       wpos += __popc(bal);
       __syncwarp();
     }
-    m = m_new;
-    r = r_new;
+    c_lt = warp_sum_i(c_lt);
+    const int c_in = wpos;
+    const int rhi = r + (two ? 1 : 0);
+    if (r >= c_lt && rhi < c_lt + c_in) {
+      if (c_in == m) { bisect = true; continue; }  // nothing dropped (ties): bisect values
+      win.wlo = lo; win.whi = hi; win.below += c_lt; win.cnt = c_in;
+      r -= c_lt; m = c_in; n_pad = 0;
+      continue;
+    }
+    // target outside the bracket: report the window that holds it
+    if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
+    else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below += c_lt + c_in; win.cnt = m_real - c_lt - c_in; }
+    else {  // the pair straddles a bracket edge (r+1 is the first key at/after the edge)
+      win.straddle = true;
+      win.split = (r + 1 == c_lt) ? lo : hi + 1u;
+      win.cnt = m_real;
+    }
+    return false;
   }
   uint32_t s[2];
   s[0] = (lane < m) ? buf[lane] : kKeyInvalid;
@@ -212,6 +273,7 @@ __device__ __noinline__ void warp_select_smem(uint32_t* buf, int m, int r, bool 
   warp_bitonic<2>(s, lane);
   k0 = warp_sorted_at<2>(s, r);
   k1 = two ? warp_sorted_at<2>(s, r + 1) : k0;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------

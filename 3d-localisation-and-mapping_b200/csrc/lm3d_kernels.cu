@@ -31,9 +31,11 @@ namespace lm3d {
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallMaxPix = 8192;       // warp-per-box up to this rect area
 constexpr int kSmallWarps = 8;           // warps per CTA in the small kernel
-constexpr int kSmallCap = 1536;          // candidate keys per warp (6 KB)
+constexpr int kSmallCap = 2048;          // candidate keys per warp (8 KB): 64 per lane, ragged
 constexpr int kSmallChunk = 2;           // boxes claimed per atomic
+constexpr int kSmallSample64Max = 3072;  // rects up to this area bracket from 64 samples, else 256
 constexpr float kBracketZ = 3.0f;        // bracket half-width in sample sigmas
+constexpr float kBracketZBig = 2.5f;     // ... for the 256-sample brackets of the bigger warp boxes
 
 constexpr int kLargeThreads = 256;
 constexpr int kLargeWarps = kLargeThreads / 32;
@@ -43,10 +45,16 @@ constexpr int kSortCap = 4096;           // block bitonic capacity (16 KB)
 struct Workspace {
   FrameTab* tab;        // [F]
   int32_t* box_frame;   // [B]
-  int32_t* small_list;  // [B]
+  void* small_items;    // [B] WorkItem (80 B): everything a warp needs for one box, one load level
   int32_t* large_list;  // [B]
   int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor
 };
+
+struct __align__(16) WorkItem {
+  int32_t b, f, x0, y0, x1, y1, pad0, pad1;
+  FrameTab tab;
+};
+static_assert(sizeof(WorkItem) == 80, "WorkItem layout");
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -60,13 +68,13 @@ static size_t workspace_layout(int64_t F, int64_t B, char* base, Workspace* ws) 
   char* c = take(64);
   char* t = take((size_t)F * sizeof(FrameTab));
   char* bf = take((size_t)B * 4);
-  char* sl = take((size_t)B * 4);
+  char* sl = take((size_t)B * 80);
   char* ll = take((size_t)B * 4);
   if (ws) {
     ws->counters = (int32_t*)c;
     ws->tab = (FrameTab*)t;
     ws->box_frame = (int32_t*)bf;
-    ws->small_list = (int32_t*)sl;
+    ws->small_items = (void*)sl;
     ws->large_list = (int32_t*)ll;
   }
   return off;
@@ -114,18 +122,21 @@ __device__ __forceinline__ int64_t csr_find(const int64_t* __restrict__ off, int
 }
 
 __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64_t* __restrict__ frame_off,
-                                  int64_t F, int64_t B, int H, int W, int32_t* __restrict__ box_frame,
-                                  int32_t* __restrict__ small_list, int32_t* __restrict__ large_list,
-                                  int32_t* __restrict__ counters) {
+                                  int64_t F, int64_t B, int H, int W, const FrameTab* __restrict__ tab,
+                                  int32_t* __restrict__ box_frame, WorkItem* __restrict__ small_items,
+                                  int32_t* __restrict__ large_list, int32_t* __restrict__ counters) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool is_small = false, is_large = false;
+  int f = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   if (b < B) {
-    box_frame[b] = (int32_t)csr_find(frame_off, F, b);
+    f = (int)csr_find(frame_off, F, b);
+    box_frame[b] = f;
     const int4 r = reinterpret_cast<const int4*>(rect4)[b];
     const int xa = min(max(r.x, 0), W - 1), xb = min(max(r.z, 0), W - 1);
     const int ya = min(max(r.y, 0), H - 1), yb = min(max(r.w, 0), H - 1);
-    const int64_t area = (int64_t)(abs(xb - xa) + 1) * (abs(yb - ya) + 1);
+    x0 = min(xa, xb); x1 = max(xa, xb); y0 = min(ya, yb); y1 = max(ya, yb);
+    const int64_t area = (int64_t)(x1 - x0 + 1) * (y1 - y0 + 1);
     is_small = area <= kSmallMaxPix;
     is_large = !is_small;
   }
@@ -139,7 +150,15 @@ __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64
   bs = __shfl_sync(kFull, bs, 0);
   bl = __shfl_sync(kFull, bl, 0);
   const uint32_t lt = lanemask_lt();
-  if (is_small) small_list[bs + __popc(ms & lt)] = (int32_t)b;
+  if (is_small) {
+    int4* dst = reinterpret_cast<int4*>(small_items + bs + __popc(ms & lt));
+    const float4* tp = reinterpret_cast<const float4*>(tab + f);
+    dst[0] = make_int4((int)b, f, x0, y0);
+    dst[1] = make_int4(x1, y1, 0, 0);
+    reinterpret_cast<float4*>(dst)[2] = tp[0];
+    reinterpret_cast<float4*>(dst)[3] = tp[1];
+    reinterpret_cast<float4*>(dst)[4] = tp[2];
+  }
   if (is_large) large_list[bl + __popc(ml & lt)] = (int32_t)b;
 }
 
@@ -168,12 +187,27 @@ __global__ void scale_boxes_kernel(const double* __restrict__ boxes, const doubl
 // ------------------------------------------------------------------------------------------
 // shared launch parameters
 // ------------------------------------------------------------------------------------------
+// Debug-only bounds checks (make DEBUG=1 -> liblm3d_dbg.so): a bad access is recorded, not executed.
+#ifdef LM3D_DEBUG_BOUNDS
+__device__ int g_dbg[16];
+__device__ __forceinline__ void dbg_report(int code, long long a, long long b, long long c) {
+  if (atomicCAS(&g_dbg[0], 0, code) == 0) {
+    g_dbg[1] = (int)a; g_dbg[2] = (int)b; g_dbg[3] = (int)c; g_dbg[4] = (int)(a >> 32);
+  }
+}
+#define LM3D_LDG(base, off, limit, code, x, y) \
+  (((unsigned long long)(off) < (unsigned long long)(limit)) ? __ldg((base) + (off)) : (dbg_report(code, off, x, y), 0.f))
+#else
+#define LM3D_LDG(base, off, limit, code, x, y) __ldg((base) + (off))
+#endif
+
 struct LiftArgs {
   const float* depth;
   const int32_t* rect4;
   const int32_t* box_frame;
   const FrameTab* tab;
   const int32_t* list;
+  const void* items;
   int32_t* counters;
   int count_idx, cursor_idx;
   int H, W;
@@ -219,7 +253,7 @@ __device__ __forceinline__ LaneMap lane_map(int w, int lane) {
   return m;
 }
 
-// Generic warp walk over the keys of a rect (used by the rare slow path only).
+// Generic warp walk over the keys of a rect (used by the rare fallback path only).
 template <typename Fn>
 __device__ __forceinline__ void warp_for_each_key(const float* __restrict__ fbase, int W, const Rect& rc,
                                                   uint32_t dmax_bits, int lane, Fn&& fn) {
@@ -237,76 +271,82 @@ __device__ __forceinline__ void warp_for_each_key(const float* __restrict__ fbas
   }
 }
 
-// Slow path: bisect the key range with counting passes over the rect until the window holds
-// <= kSmallCap keys, collect them, finish in shared memory.  Always terminates (<= 32 passes).
+// Fallback: the target ranks are known to live in `win`; re-read those keys from global
+// memory.  Windows holding more than kSmallCap keys are bisected by value first (counting
+// passes); always terminates (<= 32 bisections, every smem failure shrinks the window).
 __device__ __noinline__ void warp_select_global(const float* __restrict__ fbase, int W, const Rect& rc,
-                                                uint32_t dmax_bits, int lane, uint32_t* cand, uint32_t wlo,
-                                                uint32_t whi, int below, int cnt, int r, bool two,
-                                                uint32_t& k0, uint32_t& k1) {
+                                                uint32_t dmax_bits, int lane, uint32_t* cand, SelWindow win,
+                                                int r, bool two, uint32_t& k0, uint32_t& k1) {
   const uint32_t lt_mask = lanemask_lt();
   while (true) {
-    if (cnt <= kSmallCap) {
-      int n = 0;
-      warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
-        const bool in = (key >= wlo) && (key <= whi);
-        const uint32_t bal = __ballot_sync(kFull, in);
-        if (in) cand[n + __popc(bal & lt_mask)] = key;
-        n += __popc(bal);
-      });
-      __syncwarp();
-      warp_select_smem(cand, n, r - below, two, lane, k0, k1);
-      return;
-    }
-    if (wlo == whi) {
-      k0 = k1 = wlo;
-      return;
-    }
-    const uint32_t mid = wlo + ((whi - wlo) >> 1);
-    int c_low = 0;
-    warp_for_each_key(fbase, W, rc, dmax_bits, lane,
-                      [&](uint32_t key) { c_low += (key >= wlo) && (key <= mid); });
-    c_low = warp_sum_i(c_low);
-    const int rr = r - below;
-    if (rr + (two ? 1 : 0) < c_low) {
-      whi = mid;
-      cnt = c_low;
-    } else if (rr >= c_low) {
-      wlo = mid + 1;
-      below += c_low;
-      cnt -= c_low;
-    } else {  // rank r is the largest key <= mid, rank r+1 the smallest key > mid
+    if (win.straddle) {
       uint32_t bmax = 0u, amin = kKeyInvalid;
+      const uint32_t split = win.split;
       warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
-        if (key >= wlo && key <= mid) bmax = max(bmax, key);
-        if (key > mid && key <= whi) amin = min(amin, key);
+        if (key < split) bmax = max(bmax, key);
+        else amin = min(amin, key);
       });
       k0 = warp_max_u(bmax);
       k1 = warp_min_u(amin);
       return;
     }
+    if (win.cnt <= kSmallCap) {
+      int n = 0;
+      const uint32_t wlo = win.wlo, span = win.whi - win.wlo;
+      warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
+        const bool in = (key - wlo) <= span;
+        const uint32_t bal = __ballot_sync(kFull, in);
+        const int pos = n + __popc(bal & lt_mask);
+        if (in && pos < kSmallCap) cand[pos] = key;
+        n += __popc(bal);
+      });
+      __syncwarp();
+      win.cnt = n;               // now exact
+      if (n > kSmallCap) continue;  // the caller's count was too low: bisect instead
+      if (warp_select_smem(cand, n, 0, r - win.below, two, lane, win, k0, k1)) return;
+      continue;
+    }
+    if (win.wlo == win.whi) {
+      k0 = k1 = win.wlo;
+      return;
+    }
+    const uint32_t wlo = win.wlo, mid = win.wlo + ((win.whi - win.wlo) >> 1);
+    int c_low = 0;
+    warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) { c_low += (key - wlo) <= (mid - wlo); });
+    c_low = warp_sum_i(c_low);
+    const int rr = r - win.below;
+    if (rr + (two ? 1 : 0) < c_low) { win.whi = mid; win.cnt = c_low; }
+    else if (rr >= c_low) { win.wlo = mid + 1; win.below += c_low; win.cnt -= c_low; }
+    else { win.straddle = true; win.split = mid + 1u; }
   }
 }
 
-template <int S_E>  // sample = 32*S_E keys
+// Sample 32*S_E pixels on a lattice of the rect, sort them, and bracket the target quantile.
+template <int S_E>
 __device__ __forceinline__ void small_sample_bracket(const float* __restrict__ fbase, int W, const Rect& rc,
-                                                     int n_pix, uint32_t dmax_bits, double quant, int lane,
+                                                     int n_pix, uint32_t dmax_bits, double quant, float z, int lane,
                                                      uint32_t& lo, uint32_t& hi, bool& exact, int& sv_out,
                                                      uint32_t (&s)[S_E]) {
   constexpr int S = 32 * S_E;
+  constexpr int LC = (S_E == 2) ? 8 : 16, LR = S / LC;  // lattice: LC columns x LR rows
   exact = n_pix <= S;
   int sv = 0;
 #pragma unroll
   for (int e = 0; e < S_E; ++e) {
     const int i = e * 32 + lane;
-    int idx;
+    int ry, cx;
     bool ok = true;
-    if (exact) { idx = i; ok = i < n_pix; }
-    else idx = (int)(((long long)i * n_pix + (n_pix >> 1)) / S);
-    uint32_t bits = 0u;
-    if (ok) {
-      const int ry = idx / rc.w, cx = idx - ry * rc.w;
-      bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+    if (exact) {
+      ok = i < n_pix;
+      ry = i / rc.w;
+      cx = i - ry * rc.w;
+    } else {
+      const int ic = i % LC, ir = i / LC;
+      cx = ((2 * ic + 1) * rc.w) / (2 * LC);
+      ry = ((2 * ir + 1) * rc.h) / (2 * LR);
     }
+    uint32_t bits = 0u;
+    if (ok) bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
     const bool v = key_valid(bits, dmax_bits);
     s[e] = v ? bits : kKeyInvalid;
     sv += v;
@@ -319,35 +359,92 @@ __device__ __forceinline__ void small_sample_bracket(const float* __restrict__ f
     return;
   }
   int a, b;
-  bracket_ranks(sv, quant, kBracketZ, a, b);
+  bracket_ranks(sv, quant, z, a, b);
   const uint32_t sa = warp_sorted_at<S_E>(s, max(a, 0));
   const uint32_t sb = warp_sorted_at<S_E>(s, min(max(b, 0), S - 1));
   lo = (a < 0 || sv == 0) ? 1u : sa;
   hi = (b >= sv || sv == 0) ? kKeyMaxValid : sb;
 }
 
-__global__ void __launch_bounds__(kSmallWarps * 32) lift_small_kernel(const LiftArgs A) {
+// Accumulators of the fused pass (per lane)
+struct Acc {
+  float mn0, mn1, mn2, mx0, mx1, mx2;
+  float s0, sv;
+  float n_valid;  // counted in fp32 (exact below 2^24 per lane; a lane sees at most a few thousand pixels)
+  int c_lt;
+};
+
+// Predicated append to the lane's private candidate column (stride 128 B): no branch, and the
+// pointer saturates at the lane's last slot, which doubles as the overflow sink.
+__device__ __forceinline__ void cand_push(uint32_t& cptr, uint32_t cend, uint32_t key, uint32_t t, uint32_t span) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ls.u32 p, %2, %3;\n\t"
+      "@p st.shared.u32 [%0], %1;\n\t"
+      "@p add.u32 %0, %0, 128;\n\t"
+      "@p min.u32 %0, %0, %4;\n\t"
+      "}"
+      : "+r"(cptr)
+      : "r"(key), "r"(t), "r"(span), "r"(cend)
+      : "memory");
+}
+
+// One pixel PAIR (two rows of the lane's column).  Invalid pixels become the key 0x7fffffff:
+// as a float it is a NaN (dropped by FMNMX3), as a key it is above every bracket.
+__device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint32_t dmaxA, uint32_t dmaxB, f32x2 vr2,
+                                           f32x2 b0, f32x2 b1, f32x2 b2, f32x2 c0, f32x2 c1, f32x2 c2, uint32_t lo,
+                                           uint32_t span, Acc& A, uint32_t& cptr, uint32_t cend) {
+  const bool vA = key_valid(bitsA, dmaxA), vB = key_valid(bitsB, dmaxB);
+  const uint32_t keyA = vA ? bitsA : 0x7fffffffu, keyB = vB ? bitsB : 0x7fffffffu;
+  const f32x2 dn = pack2(__uint_as_float(keyA), __uint_as_float(keyB));
+  float xa, xb;
+  f32x2 m;
+  m = mul2(dn, fma2(b0, vr2, c0)); unpack2(m, xa, xb); A.mn0 = fmin3(A.mn0, xa, xb); A.mx0 = fmax3(A.mx0, xa, xb);
+  m = mul2(dn, fma2(b1, vr2, c1)); unpack2(m, xa, xb); A.mn1 = fmin3(A.mn1, xa, xb); A.mx1 = fmax3(A.mx1, xa, xb);
+  m = mul2(dn, fma2(b2, vr2, c2)); unpack2(m, xa, xb); A.mn2 = fmin3(A.mn2, xa, xb); A.mx2 = fmax3(A.mx2, xa, xb);
+  float vra, vrb;
+  unpack2(vr2, vra, vrb);
+  if (vA) { A.n_valid += 1.0f; A.s0 += __uint_as_float(bitsA); A.sv = fmaf(vra, __uint_as_float(bitsA), A.sv); }
+  if (vB) { A.n_valid += 1.0f; A.s0 += __uint_as_float(bitsB); A.sv = fmaf(vrb, __uint_as_float(bitsB), A.sv); }
+  const uint32_t tA = keyA - lo, tB = keyB - lo;
+  A.c_lt += (tA >> 31) + (tB >> 31);  // keys and lo are < 2^31: the difference is negative iff key < lo
+  cand_push(cptr, cend, keyA, tA, span);
+  cand_push(cptr, cend, keyB, tB, span);
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const LiftArgs A) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* cand = smem_u32 + wib * kSmallCap;
-  const uint32_t lt_mask = lanemask_lt();
+  const uint32_t cand_s = (uint32_t)__cvta_generic_to_shared(cand);
   const int n_items = A.counters[A.count_idx];
   const int W = A.W;
+  const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
 
-  while (true) {
-    int item0 = 0;
-    if (lane == 0) item0 = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);
-    item0 = __shfl_sync(kFull, item0, 0);
-    if (item0 >= n_items) break;
+  int item_next = 0;
+  if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);
+  item_next = __shfl_sync(kFull, item_next, 0);
+  while (item_next < n_items) {
+    const int item0 = item_next;
     const int item1 = min(item0 + kSmallChunk, n_items);
+    if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);  // claimed early, used late
     for (int item = item0; item < item1; ++item) {
-      const int b = A.list[item];
-      const int f = A.box_frame[b];
-      const Rect rc = load_rect(A.rect4, b, A.H, W);
+      const int4* ip = reinterpret_cast<const int4*>(items + item);
+      const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(ip + 2)), t1 = __ldg(reinterpret_cast<const float4*>(ip + 3)),
+                   t2 = __ldg(reinterpret_cast<const float4*>(ip + 4));
+      const int b = i0.x, f = i0.y;
+      Rect rc;
+      rc.x0 = i0.z; rc.y0 = i0.w; rc.x1 = i1.x; rc.y1 = i1.y;
+      rc.w = rc.x1 - rc.x0 + 1; rc.h = rc.y1 - rc.y0 + 1;
       const int n_pix = rc.w * rc.h;
       const float* __restrict__ fbase = A.depth + (size_t)f * A.H * W;
-      const float4* tp = reinterpret_cast<const float4*>(A.tab + f);
-      const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+#ifdef LM3D_DEBUG_BOUNDS
+      const uint32_t hw_lim = (uint32_t)(A.H * W);
+      if (b < 0 || f < 0 || rc.x0 < 0 || rc.y0 < 0 || rc.x1 >= W || rc.y1 >= A.H || rc.w < 1 || rc.h < 1)
+        dbg_report(10, item, b, f);
+#endif
       FrameTab tb;
       tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
       tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
@@ -357,9 +454,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32) lift_small_kernel(const Lift
       uint32_t lo, hi, ex0 = 0, ex1 = 0;
       bool exact;
       int sv;
-      if (n_pix <= 1536) {
+      if (n_pix <= kSmallSample64Max) {
         uint32_t s[2];
-        small_sample_bracket<2>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, lane, lo, hi, exact, sv, s);
+        small_sample_bracket<2>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi, exact, sv, s);
         if (exact && sv > 0) {
           int r; bool two; double g;
           order_ranks(sv, A.quant, r, two, g);
@@ -368,75 +465,87 @@ __global__ void __launch_bounds__(kSmallWarps * 32) lift_small_kernel(const Lift
         }
       } else {
         uint32_t s[8];
-        small_sample_bracket<8>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, lane, lo, hi, exact, sv, s);
+        small_sample_bracket<8>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, kBracketZBig, lane, lo, hi, exact, sv, s);
       }
 
       // ---- fused pass: unproject + pose + reduce + bracket count/collect -----------------
       const LaneMap lm = lane_map(rc.w, lane);
       const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
-      float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY;
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
-      float s0_all = 0.f, su = 0.f, sv_acc = 0.f;
-      int n_valid = 0, c_lt = 0, ncand = 0;
+      Acc acc;
+      acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
+      acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
+      acc.s0 = 0.f; acc.sv = 0.f; acc.n_valid = 0.f; acc.c_lt = 0;
+      float s0_all = 0.f, su = 0.f;
       const uint32_t span = hi - lo;
+      uint32_t cptr = cand_s + 4u * lane;
+      const uint32_t cend = cand_s + 4u * (kSmallCap - 32 + lane);  // last slot of the lane: overflow sink
+      const f32x2 b0 = pack2(tb.b[0], tb.b[0]), b1 = pack2(tb.b[1], tb.b[1]), b2 = pack2(tb.b[2], tb.b[2]);
+      const int RP = lm.RP;
+      const uint32_t rpw = (uint32_t)(RP * W);
+      const int k_full = rc.h / RP;                 // row steps every lane can take
+      const int k_all = (rc.h + RP - 1) / RP;       // row steps lane-row 0 takes
+      const f32x2 step4 = pack2((float)(4 * RP), (float)(4 * RP));
       for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
         const int cx = cx0 + lm.lc;
         const bool col_ok = cx < rc.w;
+        const uint32_t dmax_lane = col_ok ? A.dmax_bits : 0u;  // idle lanes read column 0 and drop it
         const float uf = (float)(rc.x0 + cx);
-        const float ac0 = fmaf(tb.a[0], uf, tb.c[0]), ac1 = fmaf(tb.a[1], uf, tb.c[1]),
-                    ac2 = fmaf(tb.a[2], uf, tb.c[2]);
-        const float* colp = fbase + (size_t)rc.y0 * W + rc.x0 + cx;
-        float s0 = 0.f;
-        constexpr int U = 4;
-        for (int ry0 = 0; ry0 < rc.h; ry0 += lm.RP * U) {
-          uint32_t bits[U];
-#pragma unroll
-          for (int j = 0; j < U; ++j) {
-            const int ry = ry0 + j * lm.RP + lm.lr;
-            const bool ok = col_ok && ry < rc.h;
-            bits[j] = ok ? __float_as_uint(__ldg(colp + (size_t)ry * W)) : 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < U; ++j) {
-            const int ry = ry0 + j * lm.RP + lm.lr;
-            const bool valid = key_valid(bits[j], A.dmax_bits);
-            const float d = __uint_as_float(bits[j]);
-            const float vf = (float)(rc.y0 + ry);
-            if (valid) {
-              n_valid += 1;
-              s0 += d;
-              sv_acc = fmaf(vf - vc, d, sv_acc);
-              const float m0 = d * fmaf(tb.b[0], vf, ac0);
-              const float m1 = d * fmaf(tb.b[1], vf, ac1);
-              const float m2 = d * fmaf(tb.b[2], vf, ac2);
-              mn0 = fminf(mn0, m0); mx0 = fmaxf(mx0, m0);
-              mn1 = fminf(mn1, m1); mx1 = fmaxf(mx1, m1);
-              mn2 = fminf(mn2, m2); mx2 = fmaxf(mx2, m2);
-              c_lt += (bits[j] < lo);
-            }
-            const bool in = valid && ((bits[j] - lo) <= span);
-            const uint32_t bal = __ballot_sync(kFull, in);
-            if (in) {
-              const int pos = ncand + __popc(bal & lt_mask);
-              if (pos < kSmallCap) cand[pos] = bits[j];
-            }
-            ncand += __popc(bal);
-          }
+        // column term of the ray, with the row centring folded in: a_k*u + c_k + b_k*vc
+        const float ck0 = fmaf(tb.b[0], vc, fmaf(tb.a[0], uf, tb.c[0]));
+        const float ck1 = fmaf(tb.b[1], vc, fmaf(tb.a[1], uf, tb.c[1]));
+        const float ck2 = fmaf(tb.b[2], vc, fmaf(tb.a[2], uf, tb.c[2]));
+        const f32x2 c0 = pack2(ck0, ck0), c1 = pack2(ck1, ck1), c2 = pack2(ck2, ck2);
+        const uint32_t off_safe = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx : 0));  // row 0 of the lane's column
+        uint32_t off = off_safe + (uint32_t)(lm.lr * W);
+        const float vr0 = (float)(rc.y0 + lm.lr) - vc;
+        f32x2 vrA = pack2(vr0, vr0 + (float)RP), vrB = pack2(vr0 + (float)(2 * RP), vr0 + (float)(3 * RP));
+        acc.s0 = 0.f;
+        int k = 0;
+        for (; k + 4 <= k_full; k += 4) {
+          const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
+          const uint32_t q0 = __float_as_uint(LM3D_LDG(fbase, off, hw_lim, 1, item, k)),
+                         q1 = __float_as_uint(LM3D_LDG(fbase, o1, hw_lim, 2, item, k)),
+                         q2 = __float_as_uint(LM3D_LDG(fbase, o2, hw_lim, 3, item, k)),
+                         q3 = __float_as_uint(LM3D_LDG(fbase, o3, hw_lim, 4, item, k));
+          accum_pair(q0, q1, dmax_lane, dmax_lane, vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
+          accum_pair(q2, q3, dmax_lane, dmax_lane, vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
+          off += 4 * rpw;
+          vrA = add2(vrA, step4);
+          vrB = add2(vrB, step4);
         }
-        su = fmaf(uf - uc, s0, su);
-        s0_all += s0;
+        for (; k < k_all; k += 4) {  // ragged tail: clamp the row, mask by validity ceiling
+          uint32_t q[4], dm[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ry = (k + j) * RP + lm.lr;
+            const bool ok = ry < rc.h;
+            dm[j] = ok ? dmax_lane : 0u;
+            const uint32_t oj = ok ? off + (uint32_t)j * rpw : off_safe;  // never touch rows below the rect
+            q[j] = __float_as_uint(LM3D_LDG(fbase, oj, hw_lim, 5, item, k));
+          }
+          accum_pair(q[0], q[1], dm[0], dm[1], vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
+          accum_pair(q[2], q[3], dm[2], dm[3], vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
+          off += 4 * rpw;
+          vrA = add2(vrA, step4);
+          vrB = add2(vrB, step4);
+        }
+        su = fmaf(uf - uc, acc.s0, su);
+        s0_all += acc.s0;
       }
 
       // ---- warp reduction ----------------------------------------------------------------
       BoxSums S;
-      S.n_valid = warp_sum_i(n_valid);
-      c_lt = warp_sum_i(c_lt);
+      S.n_valid = warp_sum_i((int)acc.n_valid);
+      const int c_lt = warp_sum_i(acc.c_lt);
+      const int nc = (int)((cptr - (cand_s + 4u * lane)) >> 7);  // keys this lane collected
+      const bool overflow = __any_sync(kFull, cptr == cend);     // a full column is treated as overflowed
+      const int c_in = warp_sum_i(nc);
+      const int maxc = (int)warp_max_u((uint32_t)nc);
       S.s0 = warp_sum_d((double)s0_all);
       S.su = warp_sum_d((double)su);
-      S.sv = warp_sum_d((double)sv_acc);
-      S.mn[0] = warp_min_f(mn0); S.mn[1] = warp_min_f(mn1); S.mn[2] = warp_min_f(mn2);
-      S.mx[0] = warp_max_f(mx0); S.mx[1] = warp_max_f(mx1); S.mx[2] = warp_max_f(mx2);
-      __syncwarp();
+      S.sv = warp_sum_d((double)acc.sv);
+      S.mn[0] = warp_min_f(acc.mn0); S.mn[1] = warp_min_f(acc.mn1); S.mn[2] = warp_min_f(acc.mn2);
+      S.mx[0] = warp_max_f(acc.mx0); S.mx[1] = warp_max_f(acc.mx1); S.mx[2] = warp_max_f(acc.mx2);
 
       // ---- exact order statistics --------------------------------------------------------
       uint32_t k0 = 0, k1 = 0;
@@ -447,18 +556,24 @@ __global__ void __launch_bounds__(kSmallWarps * 32) lift_small_kernel(const Lift
         if (exact) {
           k0 = ex0; k1 = ex1;
         } else {
-          const int c_in = ncand;
           const int rhi = r + (two ? 1 : 0);
-          if (r >= c_lt && rhi < c_lt + c_in && c_in <= kSmallCap) {
-            warp_select_smem(cand, c_in, r - c_lt, two, lane, k0, k1);
-          } else {
-            uint32_t wlo = 1u, whi = kKeyMaxValid;
-            int below = 0, cnt = S.n_valid;
-            if (r >= c_lt && rhi < c_lt + c_in) { wlo = lo; whi = hi; below = c_lt; cnt = c_in; }
-            else if (rhi < c_lt) { whi = lo - 1u; cnt = c_lt; }
-            else if (r >= c_lt + c_in) { wlo = hi + 1u; below = c_lt + c_in; cnt = S.n_valid - below; }
-            warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, wlo, whi, below, cnt, r, two, k0, k1);
-          }
+          SelWindow win;
+          win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = S.n_valid;
+          win.straddle = false; win.split = 0u;
+          bool done = false;
+          if (overflow) {
+            // c_in is not trustworthy: only "below lo" vs "at or above lo" is known
+            if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
+            else if (r >= c_lt) { win.wlo = lo; win.below = c_lt; win.cnt = S.n_valid - c_lt; }
+          } else if (r >= c_lt && rhi < c_lt + c_in) {
+            win.wlo = lo; win.whi = hi; win.below = c_lt; win.cnt = c_in;
+            // ragged columns -> one dense array by padding every lane up to maxc
+            for (int j = nc; j < maxc; ++j) cand[j * 32 + lane] = kKeyInvalid;
+            __syncwarp();
+            done = warp_select_smem(cand, maxc * 32, maxc * 32 - c_in, r - c_lt, two, lane, win, k0, k1);
+          } else if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
+          else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below = c_lt + c_in; win.cnt = S.n_valid - win.below; }
+          if (!done) warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, win, r, two, k0, k1);
         }
       }
       if (lane == 0)
@@ -466,6 +581,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) lift_small_kernel(const Lift
                      tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
       __syncwarp();
     }
+    item_next = __shfl_sync(kFull, item_next, 0);
   }
 }
 
@@ -839,6 +955,7 @@ static inline void prof_mark(int i, cudaStream_t st) {
 
 struct DeviceInfo {
   int sms = 0;
+  int small_ctas = 1, large_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
   bool ok = false;
   bool attrs_set = false;
 };
@@ -864,6 +981,14 @@ static int device_info(DeviceInfo** out) {
     e = cudaFuncSetAttribute(lift_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (kLargeCap + kSortCap) * 4);
     if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.small_ctas, lift_small_kernel, kSmallWarps * 32,
+                                                      kSmallWarps * kSmallCap * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.large_ctas, lift_large_kernel, kLargeThreads,
+                                                      (kLargeCap + kSortCap) * 4);
+    if (e != cudaSuccess) return (int)e;
+    d.small_ctas = std::max(d.small_ctas, 1);
+    d.large_ctas = std::max(d.large_ctas, 1);
     d.attrs_set = true;
   }
   *out = &d;
@@ -902,6 +1027,15 @@ const char* lm3d_status_string(int s) {
 }
 
 int64_t lm3d_kernel_launches(void) { return g_launches.load(); }
+
+int lm3d_debug_read(int* out16) {
+#ifdef LM3D_DEBUG_BOUNDS
+  return (int)cudaMemcpyFromSymbol(out16, g_dbg, sizeof(int) * 16);
+#else
+  (void)out16;
+  return LM3D_ERR_BAD_ARG;
+#endif
+}
 
 int lm3d_profile_enable(int on) {
   if (on && !g_prof_ev[0]) {
@@ -970,9 +1104,15 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
 
   prof_mark(0, st);
   prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, ws.tab);
+#ifdef LM3D_DEBUG_BOUNDS
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1001;
+#endif
   prof_mark(1, st);
-  prep_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, frame_off, F, B, H, W, ws.box_frame,
-                                                               ws.small_list, ws.large_list, ws.counters);
+  prep_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, frame_off, F, B, H, W, ws.tab, ws.box_frame,
+                                                               (WorkItem*)ws.small_items, ws.large_list, ws.counters);
+#ifdef LM3D_DEBUG_BOUNDS
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1002;
+#endif
   prof_mark(2, st);
   LiftArgs A;
   A.depth = depth; A.rect4 = rect4; A.box_frame = ws.box_frame; A.tab = ws.tab;
@@ -984,18 +1124,23 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
 
   // persistent grids: a multiple of the SM count, capped by the amount of work
   {
-    A.list = ws.small_list; A.count_idx = 0; A.cursor_idx = 2;
+    A.list = nullptr; A.items = ws.small_items; A.count_idx = 0; A.cursor_idx = 2;
     const int64_t want = (B + (int64_t)kSmallWarps * kSmallChunk - 1) / ((int64_t)kSmallWarps * kSmallChunk);
-    const int ctas_per_sm = 3;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * ctas_per_sm));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->small_ctas));
     lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
   }
+#ifdef LM3D_DEBUG_BOUNDS
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1003;
+#endif
   prof_mark(3, st);
   {
-    A.list = ws.large_list; A.count_idx = 1; A.cursor_idx = 3;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)dev->sms * 2));
+    A.list = ws.large_list; A.items = nullptr; A.count_idx = 1; A.cursor_idx = 3;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)dev->sms * dev->large_ctas));
     lift_large_kernel<<<grid, kLargeThreads, (kLargeCap + kSortCap) * 4, st>>>(A);
   }
+#ifdef LM3D_DEBUG_BOUNDS
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1004;
+#endif
   prof_mark(4, st);
   g_prof_valid = g_profile;
   g_launches += 4;

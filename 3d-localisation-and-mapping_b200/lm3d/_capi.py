@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblm3d.so")
+LIB_PATH = os.environ.get("LM3D_LIB", os.path.join(_HERE, "liblm3d.so"))  # LM3D_LIB: debug build only
 
 RECORD_BYTES = 96
 RECORD_WORDS = 24
