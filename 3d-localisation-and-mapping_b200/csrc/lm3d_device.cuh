@@ -237,8 +237,21 @@ __device__ __noinline__ bool warp_select_smem(uint32_t* buf, int m, int n_pad, i
     const uint32_t lo = (a < 0) ? win.wlo : min(max(sa, win.wlo), hi);
     const uint32_t span = hi - lo;
     // ---- one pass: count below, compact bracket in place ----
+    // (keys and lo are < 2^31 except the 0xffffffff padding, whose difference stays "positive")
     int c_lt = 0, wpos = 0;
-    for (int base = 0; base < m; base += 32) {
+    const int m_full = m & ~31;
+    int base = 0;
+#pragma unroll 2
+    for (; base < m_full; base += 32) {
+      const uint32_t k = buf[base + lane];
+      const uint32_t t = k - lo;
+      c_lt += (k < lo);
+      const bool in = t <= span;
+      const uint32_t bal = __ballot_sync(kFull, in);
+      if (in) buf[wpos + __popc(bal & lt_mask)] = k;
+      wpos += __popc(bal);
+    }
+    if (base < m) {
       const int i = base + lane;
       const uint32_t k = (i < m) ? buf[i] : kKeyInvalid;
       c_lt += (k < lo);
@@ -246,8 +259,8 @@ __device__ __noinline__ bool warp_select_smem(uint32_t* buf, int m, int n_pad, i
       const uint32_t bal = __ballot_sync(kFull, in);
       if (in) buf[wpos + __popc(bal & lt_mask)] = k;
       wpos += __popc(bal);
-      __syncwarp();
     }
+    __syncwarp();
     c_lt = warp_sum_i(c_lt);
     const int c_in = wpos;
     const int rhi = r + (two ? 1 : 0);

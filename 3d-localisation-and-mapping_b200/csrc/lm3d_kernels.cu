@@ -33,7 +33,7 @@ constexpr int kSmallMaxPix = 8192;       // warp-per-box up to this rect area
 constexpr int kSmallWarps = 8;           // warps per CTA in the small kernel
 constexpr int kSmallCap = 2048;          // candidate keys per warp (8 KB): 64 per lane, ragged
 constexpr int kSmallChunk = 2;           // boxes claimed per atomic
-constexpr int kSmallSample64Max = 3072;  // rects up to this area bracket from 64 samples, else 256
+constexpr int kSmallSample64Max = 4096;  // rects up to this area bracket from 64 samples, else 256
 constexpr float kBracketZ = 3.0f;        // bracket half-width in sample sigmas
 constexpr float kBracketZBig = 2.5f;     // ... for the 256-sample brackets of the bigger warp boxes
 
@@ -374,27 +374,13 @@ struct Acc {
   int c_lt;
 };
 
-// Predicated append to the lane's private candidate column (stride 128 B): no branch, and the
-// pointer saturates at the lane's last slot, which doubles as the overflow sink.
-__device__ __forceinline__ void cand_push(uint32_t& cptr, uint32_t cend, uint32_t key, uint32_t t, uint32_t span) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ls.u32 p, %2, %3;\n\t"
-      "@p st.shared.u32 [%0], %1;\n\t"
-      "@p add.u32 %0, %0, 128;\n\t"
-      "@p min.u32 %0, %0, %4;\n\t"
-      "}"
-      : "+r"(cptr)
-      : "r"(key), "r"(t), "r"(span), "r"(cend)
-      : "memory");
-}
-
 // One pixel PAIR (two rows of the lane's column).  Invalid pixels become the key 0x7fffffff:
 // as a float it is a NaN (dropped by FMNMX3), as a key it is above every bracket.
+// Keys inside the bracket are appended to the warp's dense candidate array (ballot + popc
+// compaction: no atomics, no per-lane imbalance).
 __device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint32_t dmaxA, uint32_t dmaxB, f32x2 vr2,
                                            f32x2 b0, f32x2 b1, f32x2 b2, f32x2 c0, f32x2 c1, f32x2 c2, uint32_t lo,
-                                           uint32_t span, Acc& A, uint32_t& cptr, uint32_t cend) {
+                                           uint32_t span, Acc& A, uint32_t cand_s, uint32_t lt_mask, int& ncand) {
   const bool vA = key_valid(bitsA, dmaxA), vB = key_valid(bitsB, dmaxB);
   const uint32_t keyA = vA ? bitsA : 0x7fffffffu, keyB = vB ? bitsB : 0x7fffffffu;
   const f32x2 dn = pack2(__uint_as_float(keyA), __uint_as_float(keyB));
@@ -409,8 +395,28 @@ __device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint3
   if (vB) { A.n_valid += 1.0f; A.s0 += __uint_as_float(bitsB); A.sv = fmaf(vrb, __uint_as_float(bitsB), A.sv); }
   const uint32_t tA = keyA - lo, tB = keyB - lo;
   A.c_lt += (tA >> 31) + (tB >> 31);  // keys and lo are < 2^31: the difference is negative iff key < lo
-  cand_push(cptr, cend, keyA, tA, span);
-  cand_push(cptr, cend, keyB, tB, span);
+  const bool inA = tA <= span, inB = tB <= span;
+  const uint32_t balA = __ballot_sync(kFull, inA), balB = __ballot_sync(kFull, inB);
+  const int nA = __popc(balA);
+  if (inA) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cand_s + 4u * (uint32_t)(ncand + __popc(balA & lt_mask))), "r"(keyA) : "memory");
+  if (inB) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cand_s + 4u * (uint32_t)(ncand + nA + __popc(balB & lt_mask))), "r"(keyB) : "memory");
+  ncand += nA + __popc(balB);
+}
+
+// L2 prefetch of a rect (one 128-byte line per lane per step): issued one box ahead so the
+// sample and the fused pass of the next box hit L2 instead of paying DRAM latency in-line.
+__device__ __forceinline__ void prefetch_rect_l2(const float* __restrict__ fbase, int W, int x0, int y0, int w, int h,
+                                                 int lane) {
+  const uintptr_t row0 = (uintptr_t)(fbase + (size_t)y0 * W + x0);
+  const int first = (int)((row0 & 127u) >> 2);            // element offset of x0 inside its line (row 0)
+  (void)first;
+  const int lines = ((w + 31) >> 5) + 1;                  // upper bound of lines per row
+  const int total = h * lines;
+  for (int i = lane; i < total; i += 32) {
+    const int ry = i / lines, ln = i - ry * lines;
+    const float* p = fbase + (size_t)(y0 + ry) * W + x0 + min(ln * 32, w - 1);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
 }
 
 __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const LiftArgs A) {
@@ -418,6 +424,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* cand = smem_u32 + wib * kSmallCap;
   const uint32_t cand_s = (uint32_t)__cvta_generic_to_shared(cand);
+  const uint32_t lt_mask = lanemask_lt();
   const int n_items = A.counters[A.count_idx];
   const int W = A.W;
   const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
@@ -430,6 +437,15 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
     const int item1 = min(item0 + kSmallChunk, n_items);
     if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);  // claimed early, used late
     for (int item = item0; item < item1; ++item) {
+      {  // warm L2 with the next box this warp will process
+        int nxt = item + 1;
+        if (nxt >= item1) nxt = __shfl_sync(kFull, item_next, 0);  // first box of the chunk claimed ahead
+        if (nxt < n_items) {
+          const int4* np = reinterpret_cast<const int4*>(items + nxt);
+          const int4 n0 = __ldg(np), n1 = __ldg(np + 1);
+          prefetch_rect_l2(A.depth + (size_t)n0.y * A.H * W, W, n0.z, n0.w, n1.x - n0.z + 1, n1.y - n0.w + 1, lane);
+        }
+      }
       const int4* ip = reinterpret_cast<const int4*>(items + item);
       const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
       const float4 t0 = __ldg(reinterpret_cast<const float4*>(ip + 2)), t1 = __ldg(reinterpret_cast<const float4*>(ip + 3)),
@@ -477,8 +493,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
       acc.s0 = 0.f; acc.sv = 0.f; acc.n_valid = 0.f; acc.c_lt = 0;
       float s0_all = 0.f, su = 0.f;
       const uint32_t span = hi - lo;
-      uint32_t cptr = cand_s + 4u * lane;
-      const uint32_t cend = cand_s + 4u * (kSmallCap - 32 + lane);  // last slot of the lane: overflow sink
+      int ncand = 0, c_in_done = 0;  // warp-uniform: keys in the dense array / keys dropped by overflow resets
+      bool overflow = false;
       const f32x2 b0 = pack2(tb.b[0], tb.b[0]), b1 = pack2(tb.b[1], tb.b[1]), b2 = pack2(tb.b[2], tb.b[2]);
       const int RP = lm.RP;
       const uint32_t rpw = (uint32_t)(RP * W);
@@ -507,8 +523,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
                          q1 = __float_as_uint(LM3D_LDG(fbase, o1, hw_lim, 2, item, k)),
                          q2 = __float_as_uint(LM3D_LDG(fbase, o2, hw_lim, 3, item, k)),
                          q3 = __float_as_uint(LM3D_LDG(fbase, o3, hw_lim, 4, item, k));
-          accum_pair(q0, q1, dmax_lane, dmax_lane, vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
-          accum_pair(q2, q3, dmax_lane, dmax_lane, vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
+          if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }  // uniform, rare
+          accum_pair(q0, q1, dmax_lane, dmax_lane, vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
+          accum_pair(q2, q3, dmax_lane, dmax_lane, vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
           off += 4 * rpw;
           vrA = add2(vrA, step4);
           vrB = add2(vrB, step4);
@@ -523,8 +540,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
             const uint32_t oj = ok ? off + (uint32_t)j * rpw : off_safe;  // never touch rows below the rect
             q[j] = __float_as_uint(LM3D_LDG(fbase, oj, hw_lim, 5, item, k));
           }
-          accum_pair(q[0], q[1], dm[0], dm[1], vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
-          accum_pair(q[2], q[3], dm[2], dm[3], vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cptr, cend);
+          if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }
+          accum_pair(q[0], q[1], dm[0], dm[1], vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
+          accum_pair(q[2], q[3], dm[2], dm[3], vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
           off += 4 * rpw;
           vrA = add2(vrA, step4);
           vrB = add2(vrB, step4);
@@ -537,10 +555,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
       BoxSums S;
       S.n_valid = warp_sum_i((int)acc.n_valid);
       const int c_lt = warp_sum_i(acc.c_lt);
-      const int nc = (int)((cptr - (cand_s + 4u * lane)) >> 7);  // keys this lane collected
-      const bool overflow = __any_sync(kFull, cptr == cend);     // a full column is treated as overflowed
-      const int c_in = warp_sum_i(nc);
-      const int maxc = (int)warp_max_u((uint32_t)nc);
+      const int c_in = c_in_done + ncand;
+      __syncwarp();
       S.s0 = warp_sum_d((double)s0_all);
       S.su = warp_sum_d((double)su);
       S.sv = warp_sum_d((double)acc.sv);
@@ -561,16 +577,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
           win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = S.n_valid;
           win.straddle = false; win.split = 0u;
           bool done = false;
-          if (overflow) {
-            // c_in is not trustworthy: only "below lo" vs "at or above lo" is known
-            if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
-            else if (r >= c_lt) { win.wlo = lo; win.below = c_lt; win.cnt = S.n_valid - c_lt; }
-          } else if (r >= c_lt && rhi < c_lt + c_in) {
+          if (r >= c_lt && rhi < c_lt + c_in) {
             win.wlo = lo; win.whi = hi; win.below = c_lt; win.cnt = c_in;
-            // ragged columns -> one dense array by padding every lane up to maxc
-            for (int j = nc; j < maxc; ++j) cand[j * 32 + lane] = kKeyInvalid;
-            __syncwarp();
-            done = warp_select_smem(cand, maxc * 32, maxc * 32 - c_in, r - c_lt, two, lane, win, k0, k1);
+            if (!overflow) done = warp_select_smem(cand, c_in, 0, r - c_lt, two, lane, win, k0, k1);
           } else if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
           else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below = c_lt + c_in; win.cnt = S.n_valid - win.below; }
           if (!done) warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, win, r, two, k0, k1);
