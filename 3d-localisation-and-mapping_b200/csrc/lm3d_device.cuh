@@ -157,96 +157,73 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // ---------------------------------------------------------------------------------------
 // Exact selection of ranks r (and r+1 if two) among m keys in shared memory, one warp.
 //
-// buf holds every key of the box inside the key window [wlo,whi] (plus optional 0xffffffff
-// padding, which sorts last); `below` keys of the box are smaller than the window.
-// Rounds: 32-key strided sample -> sort -> bracket -> ONE pass that counts keys below the
-// bracket and compacts the bracket in place.  If the target rank falls outside a bracket
-// the discarded keys are gone, so the routine returns false with the (now smaller) window
-// that holds the target and the caller re-reads those keys from global memory.  Rounds that
-// cannot shrink the set (heavy ties) bisect the numeric key range instead (count first).
+// buf holds every key of the box inside the key window [wlo,whi]; r is relative to buf.
+// Radix-8 select on (key - wlo): one pass counts the 8 bins in LANE-PRIVATE packed registers,
+// eight warp reductions give the bin totals, and a second pass compacts the bin holding rank
+// r in place.  Each round shrinks the value window >= 8x, so ties / degenerate data terminate
+// in <= 11 rounds; <= 64 survivors are finished with a register bitonic sort.  Never fails.
 // ---------------------------------------------------------------------------------------
 struct SelWindow {
   uint32_t wlo, whi;  // inclusive key window known to contain ranks r (and r+1)
   int below;          // keys of the box smaller than wlo
   int cnt;            // keys of the box inside the window (upper bound is fine)
-  bool straddle;      // set on failure: rank r is the largest key < split, r+1 the smallest >= split
+  bool straddle;      // rank r is the largest key < split, r+1 the smallest >= split
   uint32_t split;
 };
 
-__device__ __noinline__ bool warp_select_smem(uint32_t* buf, int m, int n_pad, int r, bool two, int lane,
-                                              SelWindow& win, uint32_t& k0, uint32_t& k1) {
-  // r is relative to the window (rank r of the box == rank r - win.below here)
+__device__ __noinline__ void warp_select_hist(uint32_t* buf, int m, int r, bool two, int lane, uint32_t wlo,
+                                              uint32_t whi, uint32_t& k0, uint32_t& k1) {
+  // Radix-8 select with the 8 bin counters of a lane packed into one 64-bit REGISTER (a lane
+  // sees <= 255 keys per round for m <= 8160), so counting is a short ALU chain: no shared
+  // histogram, no atomics.  Requires m <= 8160.
   const uint32_t lt_mask = lanemask_lt();
-  bool bisect = false;
   while (m > 64) {
-    if (bisect) {
-      // count first: the half that does not hold the target must not be destroyed blindly
-      uint32_t mn = kKeyInvalid, mx = 0u;
-      for (int i = lane; i < m; i += 32) {
-        const uint32_t k = buf[i];
-        if (k != kKeyInvalid) { mn = min(mn, k); mx = max(mx, k); }
-      }
-      mn = warp_min_u(mn);
-      mx = warp_max_u(mx);
-      if (mn >= mx) { k0 = k1 = mn; return true; }
-      const uint32_t mid = mn + ((mx - mn) >> 1);
-      int c_low = 0;
-      for (int i = lane; i < m; i += 32) c_low += (buf[i] <= mid);
-      c_low = warp_sum_i(c_low);
-      if (two && r + 1 == c_low) {  // r = largest key <= mid, r+1 = smallest key > mid
-        uint32_t bmax = 0u, amin = kKeyInvalid;
-        for (int i = lane; i < m; i += 32) {
-          const uint32_t k = buf[i];
-          if (k <= mid) bmax = max(bmax, k); else amin = min(amin, k);
-        }
-        k0 = warp_max_u(bmax);
-        k1 = warp_min_u(amin);
-        return true;
-      }
-      const bool low = r < c_low;
-      int wpos = 0;
-      for (int base = 0; base < m; base += 32) {
-        const int i = base + lane;
-        const uint32_t k = (i < m) ? buf[i] : kKeyInvalid;
-        const bool keep = (i < m) && ((k <= mid) == low) && (k != kKeyInvalid);
-        const uint32_t bal = __ballot_sync(kFull, keep);
-        if (keep) buf[wpos + __popc(bal & lt_mask)] = k;
-        wpos += __popc(bal);
-        __syncwarp();
-      }
-      if (low) { win.whi = mid; }
-      else { win.wlo = mid + 1; win.below += c_low; r -= c_low; }
-      m = wpos; n_pad = 0; win.cnt = m;
-      bisect = false;
-      continue;
-    }
-    // ---- sample 32 -> bracket ----
-    const int idx = (int)(((long long)lane * m + (m >> 1)) >> 5);
-    uint32_t s[1] = {buf[idx]};
-    warp_bitonic<1>(s, lane);
-    const int m_real = m - n_pad;
-    const float p = ((float)r + 0.5f) * (32.0f / (float)m);
-    const float fr = fminf(fmaxf(p * (1.0f / 32.0f), 0.0f), 1.0f);
-    const float delta = 2.5f * sqrtf(32.0f * fr * (1.0f - fr)) + 1.5f;
-    const int a = (int)floorf(p - delta);
-    const int b = (int)ceilf(p + 1.0f + delta);
-    const uint32_t sa = __shfl_sync(kFull, s[0], max(a, 0));
-    const uint32_t sb = __shfl_sync(kFull, s[0], min(b, 31));
-    // clamp into the window: the sample may contain 0xffffffff padding (sorts last)
-    const uint32_t hi = (b > 31) ? win.whi : max(min(sb, win.whi), win.wlo);
-    const uint32_t lo = (a < 0) ? win.wlo : min(max(sa, win.wlo), hi);
-    const uint32_t span = hi - lo;
-    // ---- one pass: count below, compact bracket in place ----
-    // (keys and lo are < 2^31 except the 0xffffffff padding, whose difference stays "positive")
-    int c_lt = 0, wpos = 0;
+    if (wlo >= whi) { k0 = k1 = wlo; return; }  // every remaining key is equal
+    const uint32_t span = whi - wlo;
+    const int shift = max(0, 29 - __clz(span));  // (span >> shift) <= 7
+    unsigned long long cnt = 0ull;
     const int m_full = m & ~31;
     int base = 0;
+#pragma unroll 4
+    for (; base < m_full; base += 32) {
+      const uint32_t bin = (buf[base + lane] - wlo) >> shift;
+      cnt += 1ull << (bin * 8u);
+    }
+    if (base + lane < m) {
+      const uint32_t bin = (buf[base + lane] - wlo) >> shift;
+      cnt += 1ull << (bin * 8u);
+    }
+    // bin totals are warp-uniform after the reductions; scan them in registers
+    int jb = -1, jb1 = -1, below = 0, keep = 0, cum = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int tot = warp_sum_i((int)((cnt >> (8 * b)) & 0xffull));
+      if (jb < 0 && cum + tot > r) { jb = b; below = cum; keep = tot; }
+      if (jb1 < 0 && cum + tot > r + (two ? 1 : 0)) jb1 = b;
+      cum += tot;
+    }
+    if (jb1 != jb) {
+      // the pair straddles two bins: rank r is the largest key of bin jb, r+1 the smallest of bin jb1
+      uint32_t bmax = 0u, amin = kKeyInvalid;
+      for (int i = lane; i < m; i += 32) {
+        const uint32_t k = buf[i];
+        const int bin = (int)((k - wlo) >> shift);
+        if (bin == jb) bmax = max(bmax, k);
+        if (bin == jb1) amin = min(amin, k);
+      }
+      k0 = warp_max_u(bmax);
+      k1 = warp_min_u(amin);
+      return;
+    }
+    // compact bin jb in place (write index never passes the read index)
+    const uint32_t nlo = wlo + ((uint32_t)jb << shift);
+    const uint32_t nspan = min(whi - nlo, (1u << shift) - 1u);
+    int wpos = 0;
+    base = 0;
 #pragma unroll 2
     for (; base < m_full; base += 32) {
       const uint32_t k = buf[base + lane];
-      const uint32_t t = k - lo;
-      c_lt += (k < lo);
-      const bool in = t <= span;
+      const bool in = (k - nlo) <= nspan;
       const uint32_t bal = __ballot_sync(kFull, in);
       if (in) buf[wpos + __popc(bal & lt_mask)] = k;
       wpos += __popc(bal);
@@ -254,31 +231,16 @@ __device__ __noinline__ bool warp_select_smem(uint32_t* buf, int m, int n_pad, i
     if (base < m) {
       const int i = base + lane;
       const uint32_t k = (i < m) ? buf[i] : kKeyInvalid;
-      c_lt += (k < lo);
-      const bool in = (k - lo) <= span;
+      const bool in = (k - nlo) <= nspan;
       const uint32_t bal = __ballot_sync(kFull, in);
       if (in) buf[wpos + __popc(bal & lt_mask)] = k;
       wpos += __popc(bal);
     }
     __syncwarp();
-    c_lt = warp_sum_i(c_lt);
-    const int c_in = wpos;
-    const int rhi = r + (two ? 1 : 0);
-    if (r >= c_lt && rhi < c_lt + c_in) {
-      if (c_in == m) { bisect = true; continue; }  // nothing dropped (ties): bisect values
-      win.wlo = lo; win.whi = hi; win.below += c_lt; win.cnt = c_in;
-      r -= c_lt; m = c_in; n_pad = 0;
-      continue;
-    }
-    // target outside the bracket: report the window that holds it
-    if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
-    else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below += c_lt + c_in; win.cnt = m_real - c_lt - c_in; }
-    else {  // the pair straddles a bracket edge (r+1 is the first key at/after the edge)
-      win.straddle = true;
-      win.split = (r + 1 == c_lt) ? lo : hi + 1u;
-      win.cnt = m_real;
-    }
-    return false;
+    r -= below;
+    m = keep;
+    wlo = nlo;
+    whi = nlo + nspan;
   }
   uint32_t s[2];
   s[0] = (lane < m) ? buf[lane] : kKeyInvalid;
@@ -286,7 +248,6 @@ __device__ __noinline__ bool warp_select_smem(uint32_t* buf, int m, int n_pad, i
   warp_bitonic<2>(s, lane);
   k0 = warp_sorted_at<2>(s, r);
   k1 = two ? warp_sorted_at<2>(s, r + 1) : k0;
-  return true;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -31,11 +31,11 @@ namespace lm3d {
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallMaxPix = 8192;       // warp-per-box up to this rect area
 constexpr int kSmallWarps = 8;           // warps per CTA in the small kernel
-constexpr int kSmallCap = 2048;          // candidate keys per warp (8 KB): 64 per lane, ragged
+constexpr int kSmallCap = 2048;          // candidate keys per warp (8 KB), dense
 constexpr int kSmallChunk = 2;           // boxes claimed per atomic
-constexpr int kSmallSample64Max = 4096;  // rects up to this area bracket from 64 samples, else 256
+constexpr int kSmallSample64Max = 4096;  // rects up to this area bracket from 64 samples, else 128
 constexpr float kBracketZ = 3.0f;        // bracket half-width in sample sigmas
-constexpr float kBracketZBig = 2.5f;     // ... for the 256-sample brackets of the bigger warp boxes
+constexpr float kBracketZBig = 2.5f;     // ... for the 128-sample brackets of the bigger warp boxes
 
 constexpr int kLargeThreads = 256;
 constexpr int kLargeWarps = kLargeThreads / 32;
@@ -272,12 +272,15 @@ __device__ __forceinline__ void warp_for_each_key(const float* __restrict__ fbas
 }
 
 // Fallback: the target ranks are known to live in `win`; re-read those keys from global
-// memory.  Windows holding more than kSmallCap keys are bisected by value first (counting
-// passes); always terminates (<= 32 bisections, every smem failure shrinks the window).
+// memory.  While the window holds more than kSmallCap keys it is narrowed by radix-8 counting
+// passes over the rect (first tightened to the min/max of the keys it actually holds), so a
+// handful of passes suffice whatever the window was; always terminates.
 __device__ __noinline__ void warp_select_global(const float* __restrict__ fbase, int W, const Rect& rc,
-                                                uint32_t dmax_bits, int lane, uint32_t* cand, SelWindow win,
-                                                int r, bool two, uint32_t& k0, uint32_t& k1) {
+                                                uint32_t dmax_bits, int lane, uint32_t* cand,
+                                                SelWindow win, int r, bool two, int32_t* stats, uint32_t& k0,
+                                                uint32_t& k1) {
   const uint32_t lt_mask = lanemask_lt();
+  if (lane == 0) atomicAdd(&stats[4], 1);
   while (true) {
     if (win.straddle) {
       uint32_t bmax = 0u, amin = kKeyInvalid;
@@ -302,22 +305,55 @@ __device__ __noinline__ void warp_select_global(const float* __restrict__ fbase,
       });
       __syncwarp();
       win.cnt = n;               // now exact
-      if (n > kSmallCap) continue;  // the caller's count was too low: bisect instead
-      if (warp_select_smem(cand, n, 0, r - win.below, two, lane, win, k0, k1)) return;
-      continue;
-    }
-    if (win.wlo == win.whi) {
-      k0 = k1 = win.wlo;
+      if (n > kSmallCap) continue;  // the caller's count was too low: narrow instead
+      warp_select_hist(cand, n, r - win.below, two, lane, win.wlo, win.whi, k0, k1);
       return;
     }
-    const uint32_t wlo = win.wlo, mid = win.wlo + ((win.whi - win.wlo) >> 1);
-    int c_low = 0;
-    warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) { c_low += (key - wlo) <= (mid - wlo); });
-    c_low = warp_sum_i(c_low);
+    if (lane == 0) atomicAdd(&stats[5], 1);
+    // tighten the window to the keys it holds, then count 8 value bins
+    {
+      uint32_t mn = kKeyInvalid, mx = 0u;
+      const uint32_t wlo = win.wlo, span = win.whi - win.wlo;
+      warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
+        if ((key - wlo) <= span) { mn = min(mn, key); mx = max(mx, key); }
+      });
+      mn = warp_min_u(mn);
+      mx = warp_max_u(mx);
+      win.wlo = mn; win.whi = mx;
+      if (mn >= mx) { k0 = k1 = mn; return; }
+    }
+    const uint32_t wlo = win.wlo, span = win.whi - win.wlo;
+    const int shift = max(0, 29 - __clz(span));
+    int c[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) c[b] = 0;
+    warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
+      const uint32_t t = key - wlo;
+      if (t <= span) {
+        const int bin = (int)(t >> shift);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) c[b] += (bin == b);
+      }
+    });
     const int rr = r - win.below;
-    if (rr + (two ? 1 : 0) < c_low) { win.whi = mid; win.cnt = c_low; }
-    else if (rr >= c_low) { win.wlo = mid + 1; win.below += c_low; win.cnt -= c_low; }
-    else { win.straddle = true; win.split = mid + 1u; }
+    int jb = -1, jb1 = -1, below = 0, keep = 0, cum = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int tot = warp_sum_i(c[b]);
+      if (jb < 0 && cum + tot > rr) { jb = b; below = cum; keep = tot; }
+      if (jb1 < 0 && cum + tot > rr + (two ? 1 : 0)) jb1 = b;
+      cum += tot;
+    }
+    if (jb1 != jb) {  // r is the largest key of bin jb, r+1 the smallest key of bin jb1 (bins between are empty)
+      win.straddle = true;
+      win.split = wlo + ((uint32_t)jb1 << shift);
+      continue;
+    }
+    const uint32_t nlo = wlo + ((uint32_t)jb << shift);
+    win.whi = min(win.whi, nlo + ((1u << shift) - 1u));
+    win.wlo = nlo;
+    win.below += below;
+    win.cnt = keep;
   }
 }
 
@@ -328,7 +364,7 @@ __device__ __forceinline__ void small_sample_bracket(const float* __restrict__ f
                                                      uint32_t& lo, uint32_t& hi, bool& exact, int& sv_out,
                                                      uint32_t (&s)[S_E]) {
   constexpr int S = 32 * S_E;
-  constexpr int LC = (S_E == 2) ? 8 : 16, LR = S / LC;  // lattice: LC columns x LR rows
+  constexpr int LC = (S_E == 2) ? 8 : (S_E == 4) ? 8 : 16, LR = S / LC;  // lattice: LC columns x LR rows
   exact = n_pix <= S;
   int sv = 0;
 #pragma unroll
@@ -407,19 +443,17 @@ __device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint3
 // sample and the fused pass of the next box hit L2 instead of paying DRAM latency in-line.
 __device__ __forceinline__ void prefetch_rect_l2(const float* __restrict__ fbase, int W, int x0, int y0, int w, int h,
                                                  int lane) {
-  const uintptr_t row0 = (uintptr_t)(fbase + (size_t)y0 * W + x0);
-  const int first = (int)((row0 & 127u) >> 2);            // element offset of x0 inside its line (row 0)
-  (void)first;
-  const int lines = ((w + 31) >> 5) + 1;                  // upper bound of lines per row
-  const int total = h * lines;
-  for (int i = lane; i < total; i += 32) {
-    const int ry = i / lines, ln = i - ry * lines;
-    const float* p = fbase + (size_t)(y0 + ry) * W + x0 + min(ln * 32, w - 1);
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  for (int ry = lane; ry < h; ry += 32) {
+    const float* rowp = fbase + (size_t)(y0 + ry) * W + x0;
+    for (int cx = 0; cx < w + 31; cx += 32)  // every 128 B line the row segment can touch
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + min(cx, w - 1)));
   }
 }
 
-__global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const LiftArgs A) {
+#ifndef LM3D_SMALL_MINB
+#define LM3D_SMALL_MINB 2
+#endif
+__global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_kernel(const LiftArgs A) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* cand = smem_u32 + wib * kSmallCap;
@@ -480,8 +514,10 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
           ex1 = two ? warp_sorted_at<2>(s, r + 1) : ex0;
         }
       } else {
-        uint32_t s[8];
-        small_sample_bracket<8>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, kBracketZBig, lane, lo, hi, exact, sv, s);
+        uint32_t s[4];
+        // the biggest warp boxes get a tighter bracket so the candidates still fit kSmallCap
+        const float z = kBracketZBig;
+        small_sample_bracket<4>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, z, lane, lo, hi, exact, sv, s);
       }
 
       // ---- fused pass: unproject + pose + reduce + bracket count/collect -----------------
@@ -577,12 +613,16 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 2) lift_small_kernel(const L
           win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = S.n_valid;
           win.straddle = false; win.split = 0u;
           bool done = false;
+          if (overflow && lane == 0) atomicAdd(&A.counters[6], 1);
           if (r >= c_lt && rhi < c_lt + c_in) {
             win.wlo = lo; win.whi = hi; win.below = c_lt; win.cnt = c_in;
-            if (!overflow) done = warp_select_smem(cand, c_in, 0, r - c_lt, two, lane, win, k0, k1);
+            if (!overflow) {
+              warp_select_hist(cand, c_in, r - c_lt, two, lane, lo, hi, k0, k1);
+              done = true;
+            }
           } else if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
           else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below = c_lt + c_in; win.cnt = S.n_valid - win.below; }
-          if (!done) warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, win, r, two, k0, k1);
+          if (!done) warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, win, r, two, A.counters, k0, k1);
         }
       }
       if (lane == 0)

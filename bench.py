@@ -306,6 +306,8 @@ def run_lm3d(args):
         kern += np.array(list(ms4))
     lib.lm3d_profile_enable(0)
     kern /= reps
+    # rare-path counters of the last call (workspace words 4..6): fallbacks, narrowing passes, overflows
+    rare = [int(v) for v in plan.workspace[:64].view(torch.int32)[4:7].cpu()]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -331,6 +333,7 @@ def run_lm3d(args):
         "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_small": kern[2], "lift_large": kern[3]},
+        "rare_paths": {"global_fallbacks": rare[0], "narrowing_passes": rare[1], "candidate_overflows": rare[2]},
     }
 
     # ---- e2e: HOST buffers through lm3d_lift_boxes_host --------------------------------------
