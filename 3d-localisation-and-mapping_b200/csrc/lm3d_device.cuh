@@ -59,37 +59,44 @@ __device__ __forceinline__ float warp_min_f(float v) { return ord2f(warp_min_u(f
 __device__ __forceinline__ float warp_max_f(float v) { return ord2f(warp_max_u(f2ord(v))); }
 
 // ---------------------------------------------------------------------------------------
-// warp bitonic sort of 32*E keys, element i lives in k[i / 32] of lane i % 32
+// warp bitonic sort of 32*E keys, element i lives in k[i / 32] of lane i % 32.
+// The shuffle stages run as a rolled loop over (size, stride): the instruction cache, not
+// the ALUs, is what a fully unrolled network (2k+ instructions) costs this kernel.
 // ---------------------------------------------------------------------------------------
 template <int E>
+__device__ __forceinline__ void bitonic_shuffle_stages(uint32_t (&k)[E], int lane, int size, int stride) {
+#pragma unroll 1
+  for (; stride > 0; stride >>= 1) {
+    const bool lower = ((lane & stride) == 0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint32_t other = __shfl_xor_sync(kFull, k[e], stride);
+      const bool up = (((e * 32 + lane) & size) == 0);
+      k[e] = (lower == up) ? min(k[e], other) : max(k[e], other);
+    }
+  }
+}
+
+template <int E>
 __device__ __forceinline__ void warp_bitonic(uint32_t (&k)[E], int lane) {
+#pragma unroll 1
+  for (int size = 2; size <= 32; size <<= 1) bitonic_shuffle_stages<E>(k, lane, size, size >> 1);
 #pragma unroll
-  for (int size = 2; size <= 32 * E; size <<= 1) {
+  for (int size = 64; size <= 32 * E; size <<= 1) {
 #pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (E > 1 && stride >= 32) {
-        const int es = stride >> 5;
+    for (int es = size >> 6; es > 0; es >>= 1) {  // in-register stages: partner = e ^ es
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          if ((e & es) == 0) {
-            const int e2 = (e | es) & (E - 1);         // (& keeps dead E==1 code in bounds)
-            const bool up = (((e * 32) & size) == 0);  // lane bits < 32 <= size never matter here
-            uint32_t lo = min(k[e], k[e2]), hi = max(k[e], k[e2]);
-            k[e] = up ? lo : hi;
-            k[e2] = up ? hi : lo;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int i = e * 32 + lane;
-          const uint32_t other = __shfl_xor_sync(kFull, k[e], stride);
-          const bool up = ((i & size) == 0);
-          const bool lower = ((lane & stride) == 0);
-          k[e] = (lower == up) ? min(k[e], other) : max(k[e], other);
+      for (int e = 0; e < E; ++e) {
+        if ((e & es) == 0) {
+          const int e2 = (e | es) & (E - 1);
+          const bool up = (((e * 32) & size) == 0);
+          const uint32_t lo = min(k[e], k[e2]), hi = max(k[e], k[e2]);
+          k[e] = up ? lo : hi;
+          k[e2] = up ? hi : lo;
         }
       }
     }
+    bitonic_shuffle_stages<E>(k, lane, size, 16);
   }
 }
 
@@ -100,6 +107,30 @@ __device__ __forceinline__ uint32_t warp_sorted_at(const uint32_t (&k)[E], int i
   for (int e = 1; e < E; ++e)
     if ((idx >> 5) == e) v = k[e];
   return __shfl_sync(kFull, v, idx & 31);
+}
+
+// ---------------------------------------------------------------------------------------
+// Bitonic sort of n (power of two >= 64) keys in shared memory by one warp: ONE rolled copy
+// of the network serves every sample size and the final sort of the select (code size is
+// what limits this kernel's issue rate).
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void warp_sort_smem(uint32_t* buf, int n, int lane) {
+  __syncwarp();
+#pragma unroll 1
+  for (int size = 2; size <= n; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll 1
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const bool up = ((i & size) == 0);
+        const uint32_t a = buf[i], b = buf[j];
+        if ((a > b) == up) { buf[i] = b; buf[j] = a; }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -195,7 +226,7 @@ __device__ __noinline__ void warp_select_hist(uint32_t* buf, int m, int r, bool 
     }
     // bin totals are warp-uniform after the reductions; scan them in registers
     int jb = -1, jb1 = -1, below = 0, keep = 0, cum = 0;
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 8; ++b) {
       const int tot = warp_sum_i((int)((cnt >> (8 * b)) & 0xffull));
       if (jb < 0 && cum + tot > r) { jb = b; below = cum; keep = tot; }
@@ -242,12 +273,13 @@ __device__ __noinline__ void warp_select_hist(uint32_t* buf, int m, int r, bool 
     wlo = nlo;
     whi = nlo + nspan;
   }
-  uint32_t s[2];
-  s[0] = (lane < m) ? buf[lane] : kKeyInvalid;
-  s[1] = (lane + 32 < m) ? buf[lane + 32] : kKeyInvalid;
-  warp_bitonic<2>(s, lane);
-  k0 = warp_sorted_at<2>(s, r);
-  k1 = two ? warp_sorted_at<2>(s, r + 1) : k0;
+  __syncwarp();
+  if (lane + m < 64) buf[lane + m] = kKeyInvalid;  // pad to 64 (m >= 1, so two 32-wide stores cover it)
+  if (lane + 32 + m < 64) buf[lane + 32 + m] = kKeyInvalid;
+  warp_sort_smem(buf, 64, lane);
+  k0 = buf[r];
+  k1 = two ? buf[r + 1] : k0;
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------

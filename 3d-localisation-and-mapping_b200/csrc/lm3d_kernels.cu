@@ -29,13 +29,11 @@ namespace lm3d {
 // ------------------------------------------------------------------------------------------
 // tunables
 // ------------------------------------------------------------------------------------------
-constexpr int kSmallMaxPix = 8192;       // warp-per-box up to this rect area
+constexpr int kSmallMaxPix = 8160;       // warp-per-box up to this rect area (255 px per lane: 8-bit packed counters)
 constexpr int kSmallWarps = 8;           // warps per CTA in the small kernel
 constexpr int kSmallCap = 2048;          // candidate keys per warp (8 KB), dense
 constexpr int kSmallChunk = 2;           // boxes claimed per atomic
-constexpr int kSmallSample64Max = 4096;  // rects up to this area bracket from 64 samples, else 128
 constexpr float kBracketZ = 3.0f;        // bracket half-width in sample sigmas
-constexpr float kBracketZBig = 2.5f;     // ... for the 128-sample brackets of the bigger warp boxes
 
 constexpr int kLargeThreads = 256;
 constexpr int kLargeWarps = kLargeThreads / 32;
@@ -324,22 +322,18 @@ __device__ __noinline__ void warp_select_global(const float* __restrict__ fbase,
     }
     const uint32_t wlo = win.wlo, span = win.whi - win.wlo;
     const int shift = max(0, 29 - __clz(span));
-    int c[8];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) c[b] = 0;
+    // 8 bin counters packed in one 64-bit register (a lane sees <= 256 keys of a warp box; the
+    // pack is flushed to the running totals before it can saturate)
+    unsigned long long cnt = 0ull;
     warp_for_each_key(fbase, W, rc, dmax_bits, lane, [&](uint32_t key) {
       const uint32_t t = key - wlo;
-      if (t <= span) {
-        const int bin = (int)(t >> shift);
-#pragma unroll
-        for (int b = 0; b < 8; ++b) c[b] += (bin == b);
-      }
+      if (t <= span) cnt += 1ull << ((t >> shift) * 8u);
     });
     const int rr = r - win.below;
     int jb = -1, jb1 = -1, below = 0, keep = 0, cum = 0;
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 8; ++b) {
-      const int tot = warp_sum_i(c[b]);
+      const int tot = warp_sum_i((int)((cnt >> (8 * b)) & 0xffull));
       if (jb < 0 && cum + tot > rr) { jb = b; below = cum; keep = tot; }
       if (jb1 < 0 && cum + tot > rr + (two ? 1 : 0)) jb1 = b;
       cum += tot;
@@ -357,49 +351,39 @@ __device__ __noinline__ void warp_select_global(const float* __restrict__ fbase,
   }
 }
 
-// Sample 32*S_E pixels on a lattice of the rect, sort them, and bracket the target quantile.
-template <int S_E>
+// Sample S = 64 / 128 / 256 pixels on an 8 x S/8 lattice of the rect into shared memory (the
+// candidate buffer is idle before the fused pass), sort them, and bracket the target quantile.
+// Bracket width ~ (z sqrt(S) + 4)/S of the rect: 44 % / 25 % / 17 %, so bigger rects take
+// bigger samples and the expected candidates (+3 sigma) stay below kSmallCap.  Rects of <= 64
+// pixels skip the sample: their bracket is "every valid key" and the select's sort finishes.
 __device__ __forceinline__ void small_sample_bracket(const float* __restrict__ fbase, int W, const Rect& rc,
-                                                     int n_pix, uint32_t dmax_bits, double quant, float z, int lane,
-                                                     uint32_t& lo, uint32_t& hi, bool& exact, int& sv_out,
-                                                     uint32_t (&s)[S_E]) {
-  constexpr int S = 32 * S_E;
-  constexpr int LC = (S_E == 2) ? 8 : (S_E == 4) ? 8 : 16, LR = S / LC;  // lattice: LC columns x LR rows
-  exact = n_pix <= S;
+                                                     int n_pix, uint32_t dmax_bits, double quant, int lane,
+                                                     uint32_t* smp, uint32_t& lo, uint32_t& hi) {
+  lo = 1u;
+  hi = kKeyMaxValid;
+  if (n_pix <= 64) return;
+  const int lg = (n_pix <= 3072) ? 3 : (n_pix <= 6144) ? 4 : 5;  // lattice rows = 8, 16, 32
+  const int S = 8 << lg;
+  const float z = (lg == 3) ? kBracketZ : 2.5f;
   int sv = 0;
-#pragma unroll
-  for (int e = 0; e < S_E; ++e) {
-    const int i = e * 32 + lane;
-    int ry, cx;
-    bool ok = true;
-    if (exact) {
-      ok = i < n_pix;
-      ry = i / rc.w;
-      cx = i - ry * rc.w;
-    } else {
-      const int ic = i % LC, ir = i / LC;
-      cx = ((2 * ic + 1) * rc.w) / (2 * LC);
-      ry = ((2 * ir + 1) * rc.h) / (2 * LR);
-    }
-    uint32_t bits = 0u;
-    if (ok) bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+#pragma unroll 1
+  for (int i = lane; i < S; i += 32) {
+    const int ic = i & 7, ir = i >> 3;
+    const int cx = ((2 * ic + 1) * rc.w) >> 4;
+    const int ry = ((2 * ir + 1) * rc.h) >> (lg + 1);
+    const uint32_t bits = __float_as_uint(__ldg(fbase + (uint32_t)((rc.y0 + ry) * W + rc.x0 + cx)));
     const bool v = key_valid(bits, dmax_bits);
-    s[e] = v ? bits : kKeyInvalid;
+    smp[i] = v ? bits : kKeyInvalid;
     sv += v;
   }
   sv = warp_sum_i(sv);
-  warp_bitonic<S_E>(s, lane);
-  sv_out = sv;
-  if (exact) {  // the "sample" is the whole box: no bracket needed
-    lo = kKeyInvalid; hi = kKeyInvalid;
-    return;
-  }
+  if (sv == 0) return;
+  warp_sort_smem(smp, S, lane);
   int a, b;
   bracket_ranks(sv, quant, z, a, b);
-  const uint32_t sa = warp_sorted_at<S_E>(s, max(a, 0));
-  const uint32_t sb = warp_sorted_at<S_E>(s, min(max(b, 0), S - 1));
-  lo = (a < 0 || sv == 0) ? 1u : sa;
-  hi = (b >= sv || sv == 0) ? kKeyMaxValid : sb;
+  if (a >= 0) lo = smp[a];
+  if (b < sv) hi = smp[b];
+  __syncwarp();
 }
 
 // Accumulators of the fused pass (per lane)
@@ -439,13 +423,13 @@ __device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint3
   ncand += nA + __popc(balB);
 }
 
-// L2 prefetch of a rect (one 128-byte line per lane per step): issued one box ahead so the
+// L2 prefetch of a rect (one 32-byte sector per lane per step): issued one box ahead so the
 // sample and the fused pass of the next box hit L2 instead of paying DRAM latency in-line.
 __device__ __forceinline__ void prefetch_rect_l2(const float* __restrict__ fbase, int W, int x0, int y0, int w, int h,
                                                  int lane) {
   for (int ry = lane; ry < h; ry += 32) {
     const float* rowp = fbase + (size_t)(y0 + ry) * W + x0;
-    for (int cx = 0; cx < w + 31; cx += 32)  // every 128 B line the row segment can touch
+    for (int cx = 0; cx < w + 7; cx += 8)  // every 32 B sector the row segment can touch
       asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + min(cx, w - 1)));
   }
 }
@@ -501,24 +485,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
       tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
 
       // ---- sample -> bracket -------------------------------------------------------------
-      uint32_t lo, hi, ex0 = 0, ex1 = 0;
-      bool exact;
-      int sv;
-      if (n_pix <= kSmallSample64Max) {
-        uint32_t s[2];
-        small_sample_bracket<2>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi, exact, sv, s);
-        if (exact && sv > 0) {
-          int r; bool two; double g;
-          order_ranks(sv, A.quant, r, two, g);
-          ex0 = warp_sorted_at<2>(s, r);
-          ex1 = two ? warp_sorted_at<2>(s, r + 1) : ex0;
-        }
-      } else {
-        uint32_t s[4];
-        // the biggest warp boxes get a tighter bracket so the candidates still fit kSmallCap
-        const float z = kBracketZBig;
-        small_sample_bracket<4>(fbase, W, rc, n_pix, A.dmax_bits, A.quant, z, lane, lo, hi, exact, sv, s);
-      }
+      uint32_t lo, hi;
+      small_sample_bracket(fbase, W, rc, n_pix, A.dmax_bits, A.quant, lane, cand, lo, hi);
 
       // ---- fused pass: unproject + pose + reduce + bracket count/collect -----------------
       const LaneMap lm = lane_map(rc.w, lane);
@@ -552,31 +520,27 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
         const float vr0 = (float)(rc.y0 + lm.lr) - vc;
         f32x2 vrA = pack2(vr0, vr0 + (float)RP), vrB = pack2(vr0 + (float)(2 * RP), vr0 + (float)(3 * RP));
         acc.s0 = 0.f;
-        int k = 0;
-        for (; k + 4 <= k_full; k += 4) {
-          const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
-          const uint32_t q0 = __float_as_uint(LM3D_LDG(fbase, off, hw_lim, 1, item, k)),
-                         q1 = __float_as_uint(LM3D_LDG(fbase, o1, hw_lim, 2, item, k)),
-                         q2 = __float_as_uint(LM3D_LDG(fbase, o2, hw_lim, 3, item, k)),
-                         q3 = __float_as_uint(LM3D_LDG(fbase, o3, hw_lim, 4, item, k));
-          if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }  // uniform, rare
-          accum_pair(q0, q1, dmax_lane, dmax_lane, vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
-          accum_pair(q2, q3, dmax_lane, dmax_lane, vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
-          off += 4 * rpw;
-          vrA = add2(vrA, step4);
-          vrB = add2(vrB, step4);
-        }
-        for (; k < k_all; k += 4) {  // ragged tail: clamp the row, mask by validity ceiling
+#pragma unroll 1
+        for (int k = 0; k < k_all; k += 4) {
           uint32_t q[4], dm[4];
+          if (k + 4 <= k_full) {  // warp-uniform: every lane owns all four rows of this group
+            const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
+            q[0] = __float_as_uint(LM3D_LDG(fbase, off, hw_lim, 1, item, k));
+            q[1] = __float_as_uint(LM3D_LDG(fbase, o1, hw_lim, 2, item, k));
+            q[2] = __float_as_uint(LM3D_LDG(fbase, o2, hw_lim, 3, item, k));
+            q[3] = __float_as_uint(LM3D_LDG(fbase, o3, hw_lim, 4, item, k));
+            dm[0] = dm[1] = dm[2] = dm[3] = dmax_lane;
+          } else {  // ragged tail: clamp the row, mask by validity ceiling
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ry = (k + j) * RP + lm.lr;
-            const bool ok = ry < rc.h;
-            dm[j] = ok ? dmax_lane : 0u;
-            const uint32_t oj = ok ? off + (uint32_t)j * rpw : off_safe;  // never touch rows below the rect
-            q[j] = __float_as_uint(LM3D_LDG(fbase, oj, hw_lim, 5, item, k));
+            for (int j = 0; j < 4; ++j) {
+              const int ry = (k + j) * RP + lm.lr;
+              const bool ok = ry < rc.h;
+              dm[j] = ok ? dmax_lane : 0u;
+              const uint32_t oj = ok ? off + (uint32_t)j * rpw : off_safe;  // never touch rows below the rect
+              q[j] = __float_as_uint(LM3D_LDG(fbase, oj, hw_lim, 5, item, k));
+            }
           }
-          if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }
+          if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }  // uniform, rare
           accum_pair(q[0], q[1], dm[0], dm[1], vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
           accum_pair(q[2], q[3], dm[2], dm[3], vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
           off += 4 * rpw;
@@ -605,9 +569,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
       if (S.n_valid > 0) {
         int r; bool two;
         order_ranks(S.n_valid, A.quant, r, two, gamma);
-        if (exact) {
-          k0 = ex0; k1 = ex1;
-        } else {
+        {
           const int rhi = r + (two ? 1 : 0);
           SelWindow win;
           win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = S.n_valid;
