@@ -192,7 +192,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // Radix-8 select on (key - wlo): one pass counts the 8 bins in LANE-PRIVATE packed registers,
 // eight warp reductions give the bin totals, and a second pass compacts the bin holding rank
 // r in place.  Each round shrinks the value window >= 8x, so ties / degenerate data terminate
-// in <= 11 rounds; <= 64 survivors are finished with a register bitonic sort.  Never fails.
+// in <= 11 rounds; <= 32 survivors are finished with a one-register bitonic sort.  Never fails.
 // ---------------------------------------------------------------------------------------
 struct SelWindow {
   uint32_t wlo, whi;  // inclusive key window known to contain ranks r (and r+1)
@@ -208,7 +208,7 @@ __device__ __noinline__ void warp_select_hist(uint32_t* buf, int m, int r, bool 
   // sees <= 255 keys per round for m <= 8160), so counting is a short ALU chain: no shared
   // histogram, no atomics.  Requires m <= 8160.
   const uint32_t lt_mask = lanemask_lt();
-  while (m > 64) {
+  while (m > 32) {
     if (wlo >= whi) { k0 = k1 = wlo; return; }  // every remaining key is equal
     const uint32_t span = whi - wlo;
     const int shift = max(0, 29 - __clz(span));  // (span >> shift) <= 7
@@ -273,12 +273,10 @@ __device__ __noinline__ void warp_select_hist(uint32_t* buf, int m, int r, bool 
     wlo = nlo;
     whi = nlo + nspan;
   }
-  __syncwarp();
-  if (lane + m < 64) buf[lane + m] = kKeyInvalid;  // pad to 64 (m >= 1, so two 32-wide stores cover it)
-  if (lane + 32 + m < 64) buf[lane + 32 + m] = kKeyInvalid;
-  warp_sort_smem(buf, 64, lane);
-  k0 = buf[r];
-  k1 = two ? buf[r + 1] : k0;
+  uint32_t s1[1] = {(lane < m) ? buf[lane] : kKeyInvalid};
+  warp_bitonic<1>(s1, lane);
+  k0 = __shfl_sync(kFull, s1[0], r);
+  k1 = two ? __shfl_sync(kFull, s1[0], r + 1) : k0;
   __syncwarp();
 }
 

@@ -351,26 +351,48 @@ __device__ __noinline__ void warp_select_global(const float* __restrict__ fbase,
   }
 }
 
-// Sample S = 64 / 128 / 256 pixels on an 8 x S/8 lattice of the rect into shared memory (the
-// candidate buffer is idle before the fused pass), sort them, and bracket the target quantile.
-// Bracket width ~ (z sqrt(S) + 4)/S of the rect: 44 % / 25 % / 17 %, so bigger rects take
-// bigger samples and the expected candidates (+3 sigma) stay below kSmallCap.  Rects of <= 64
-// pixels skip the sample: their bracket is "every valid key" and the select's sort finishes.
-__device__ __forceinline__ void small_sample_bracket(const float* __restrict__ fbase, int W, const Rect& rc,
-                                                     int n_pix, uint32_t dmax_bits, double quant, int lane,
-                                                     uint32_t* smp, uint32_t& lo, uint32_t& hi) {
-  lo = 1u;
-  hi = kKeyMaxValid;
-  if (n_pix <= 64) return;
-  const int lg = (n_pix <= 3072) ? 3 : (n_pix <= 6144) ? 4 : 5;  // lattice rows = 8, 16, 32
-  const int S = 8 << lg;
-  const float z = (lg == 3) ? kBracketZ : 2.5f;
+// Sample S = 32*E pixels on an 8 x 4E lattice of the rect, sort them in registers (rolled
+// shuffle network) and bracket the target quantile.  Bracket width ~ (z sqrt(S) + 4)/S of the
+// rect: 44 % / 25 % for S = 64 / 128.
+template <int E>
+__device__ __forceinline__ void sample_bracket_regs(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                    uint32_t dmax_bits, double quant, float z, int lane,
+                                                    uint32_t& lo, uint32_t& hi) {
+  uint32_t s[E];
   int sv = 0;
-#pragma unroll 1
-  for (int i = lane; i < S; i += 32) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
     const int ic = i & 7, ir = i >> 3;
     const int cx = ((2 * ic + 1) * rc.w) >> 4;
-    const int ry = ((2 * ir + 1) * rc.h) >> (lg + 1);
+    const int ry = ((2 * ir + 1) * rc.h) / (8 * E);
+    const uint32_t bits = __float_as_uint(__ldg(fbase + (uint32_t)((rc.y0 + ry) * W + rc.x0 + cx)));
+    const bool v = key_valid(bits, dmax_bits);
+    s[e] = v ? bits : kKeyInvalid;
+    sv += v;
+  }
+  sv = warp_sum_i(sv);
+  if (sv == 0) return;
+  warp_bitonic<E>(s, lane);
+  int a, b;
+  bracket_ranks(sv, quant, z, a, b);
+  const uint32_t sa = warp_sorted_at<E>(s, max(a, 0));
+  const uint32_t sb = warp_sorted_at<E>(s, min(max(b, 0), 32 * E - 1));
+  if (a >= 0) lo = sa;
+  if (b < sv) hi = sb;
+}
+
+// The biggest warp boxes (5 % of config C2) take 256 samples through shared memory (the
+// candidate buffer is idle before the fused pass) and the rolled shared-memory sort: 17 %.
+__device__ __noinline__ void sample_bracket_smem(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                 uint32_t dmax_bits, double quant, float z, int lane, uint32_t* smp,
+                                                 uint32_t& lo, uint32_t& hi) {
+  int sv = 0;
+#pragma unroll 1
+  for (int i = lane; i < 256; i += 32) {
+    const int ic = i & 7, ir = i >> 3;
+    const int cx = ((2 * ic + 1) * rc.w) >> 4;
+    const int ry = ((2 * ir + 1) * rc.h) >> 6;
     const uint32_t bits = __float_as_uint(__ldg(fbase + (uint32_t)((rc.y0 + ry) * W + rc.x0 + cx)));
     const bool v = key_valid(bits, dmax_bits);
     smp[i] = v ? bits : kKeyInvalid;
@@ -378,12 +400,26 @@ __device__ __forceinline__ void small_sample_bracket(const float* __restrict__ f
   }
   sv = warp_sum_i(sv);
   if (sv == 0) return;
-  warp_sort_smem(smp, S, lane);
+  warp_sort_smem(smp, 256, lane);
   int a, b;
   bracket_ranks(sv, quant, z, a, b);
   if (a >= 0) lo = smp[a];
   if (b < sv) hi = smp[b];
   __syncwarp();
+}
+
+// Rects of <= 32 pixels skip the sample: their bracket is "every valid key", so all of them
+// are collected and the select's final sort finishes the job.  Bigger rects take bigger
+// samples so that the expected candidates (+3 sigma) stay below kSmallCap.
+__device__ __forceinline__ void small_sample_bracket(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                     int n_pix, uint32_t dmax_bits, double quant, int lane,
+                                                     uint32_t* smp, uint32_t& lo, uint32_t& hi) {
+  lo = 1u;
+  hi = kKeyMaxValid;
+  if (n_pix <= 32) return;
+  if (n_pix <= 3072) sample_bracket_regs<2>(fbase, W, rc, dmax_bits, quant, kBracketZ, lane, lo, hi);
+  else if (n_pix <= 6144) sample_bracket_regs<4>(fbase, W, rc, dmax_bits, quant, 2.5f, lane, lo, hi);
+  else sample_bracket_smem(fbase, W, rc, dmax_bits, quant, 2.5f, lane, smp, lo, hi);
 }
 
 // Accumulators of the fused pass (per lane)
