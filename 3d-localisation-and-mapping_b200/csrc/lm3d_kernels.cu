@@ -459,17 +459,6 @@ __device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint3
   ncand += nA + __popc(balB);
 }
 
-// L2 prefetch of a rect (one 32-byte sector per lane per step): issued one box ahead so the
-// sample and the fused pass of the next box hit L2 instead of paying DRAM latency in-line.
-__device__ __forceinline__ void prefetch_rect_l2(const float* __restrict__ fbase, int W, int x0, int y0, int w, int h,
-                                                 int lane) {
-  for (int ry = lane; ry < h; ry += 32) {
-    const float* rowp = fbase + (size_t)(y0 + ry) * W + x0;
-    for (int cx = 0; cx < w + 7; cx += 8)  // every 32 B sector the row segment can touch
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + min(cx, w - 1)));
-  }
-}
-
 #ifndef LM3D_SMALL_MINB
 #define LM3D_SMALL_MINB 2
 #endif
@@ -491,15 +480,6 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
     const int item1 = min(item0 + kSmallChunk, n_items);
     if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);  // claimed early, used late
     for (int item = item0; item < item1; ++item) {
-      {  // warm L2 with the next box this warp will process
-        int nxt = item + 1;
-        if (nxt >= item1) nxt = __shfl_sync(kFull, item_next, 0);  // first box of the chunk claimed ahead
-        if (nxt < n_items) {
-          const int4* np = reinterpret_cast<const int4*>(items + nxt);
-          const int4 n0 = __ldg(np), n1 = __ldg(np + 1);
-          prefetch_rect_l2(A.depth + (size_t)n0.y * A.H * W, W, n0.z, n0.w, n1.x - n0.z + 1, n1.y - n0.w + 1, lane);
-        }
-      }
       const int4* ip = reinterpret_cast<const int4*>(items + item);
       const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
       const float4 t0 = __ldg(reinterpret_cast<const float4*>(ip + 2)), t1 = __ldg(reinterpret_cast<const float4*>(ip + 3)),
