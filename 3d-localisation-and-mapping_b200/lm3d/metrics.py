@@ -4,12 +4,14 @@ from __future__ import annotations
 import torch
 
 
-def union_pixels(rect4: torch.Tensor, frame_off: torch.Tensor, H: int, W: int, chunk: int = 1024) -> torch.Tensor:
+def union_pixels(rect4: torch.Tensor, frame_off: torch.Tensor, H: int, W: int, chunk: int | None = None) -> torch.Tensor:
     """``U_f`` = number of distinct pixels covered by >=1 rect of frame f, exactly, via a 2-D
     difference array per frame (int32 ``[chunk,H+1,W+1]`` on the rects' device)."""
     F = frame_off.numel() - 1
     dev = rect4.device
     B = rect4.shape[0]
+    if chunk is None:  # ~256 MB of int32 difference array per chunk
+        chunk = max(1, min(1024, (1 << 26) // ((H + 1) * (W + 1))))
     box_frame = torch.searchsorted(frame_off[1:].contiguous(), torch.arange(B, device=dev), right=True)
     U = torch.zeros(F, dtype=torch.int64, device=dev)
     r = rect4.long()

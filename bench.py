@@ -34,7 +34,7 @@ for _p in (ROOT, os.path.join(ROOT, "3d-localisation-and-mapping_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-WORKLOAD = "C2"
+WORKLOAD = "C2"  # the config BASELINE.json's metric is quoted on; --workload picks another (diagnostics only)
 METRIC = "frames_per_s_lifted"
 UNIT = "frames/s"
 
@@ -211,6 +211,47 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def run_e2e(args, torch, lift, tensors, nb, local, barrier, max_over_ranks, frames_total, plan):
+    """Same metric through the reference-facing HOST-buffer call: pinned host inputs -> H2D -> lift ->
+    D2H of the records, every step, all inside the timed region (wall clock around the blocking call)."""
+    def pinned(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+
+    host = [pinned(t) for t in tensors]
+    h_out_t = torch.empty((nb, 24), dtype=torch.float32, pin_memory=True)
+    h_out = h_out_t.numpy().view(lift.RECORD_DTYPE).reshape(-1)
+    torch.cuda.synchronize()
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = nb * 96
+    arrs = [t.numpy() for t in host]
+
+    def e2e_step():
+        lift.lift_boxes_host(*arrs, device=local, out=h_out)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    # the host entry and the device entry must agree byte for byte (same deterministic kernels)
+    dev_rec = lift.records_to_numpy(plan.records[:nb])
+    return {
+        "value": frames_total / e2e_s,
+        "unit": UNIT,
+        "h2d_bytes_per_step": h2d,
+        "d2h_bytes_per_step": d2h,
+        "api": "lm3d_lift_boxes_host (pinned host buffers, chunked H2D overlapped with compute)",
+        "steps": e2e_steps,
+        "matches_device_path": bool(dev_rec.tobytes() == h_out.tobytes()),
+    }
+
+
 def run_lm3d(args):
     import numpy as np
     import torch
@@ -251,10 +292,12 @@ def run_lm3d(args):
         return float(t.item())
 
     # ---- workload: one C2-shaped shard per GPU, generated in HBM (untimed) -------------------
-    F, H, W, B = synth.CONFIGS[WORKLOAD]
+    workload = args.workload
+    F, H, W, B = synth.CONFIGS[workload]
     if args.frames:
         F = args.frames
-    data = synth.make_sequence_torch(F, H, W, B, seed=1234 + 2 + 1000 * rank, device=dev)
+    data = synth.make_sequence_torch(F, H, W, B, seed=1234 + int(workload[1:]) + 1000 * rank, device=dev,
+                                     chunk=512 if H * W < 1_000_000 else 8)
     depth, pose7, intr4 = data["depth"], data["pose7"], data["intr4"]
     boxes, image_wh, frame_off = data["boxes"], data["image_wh"], data["frame_off"]
     nb = boxes.shape[0]
@@ -319,7 +362,7 @@ def run_lm3d(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(WORKLOAD if not args.frames else "", None)
+            traffic = json.load(open(tpath)).get(workload if not args.frames else "", None)
         except Exception:
             traffic = None
     roofline = {
@@ -337,39 +380,10 @@ def run_lm3d(args):
     }
 
     # ---- e2e: HOST buffers through lm3d_lift_boxes_host --------------------------------------
-    def pinned(t):
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        h.copy_(t)
-        return h
-
-    h_depth, h_pose, h_intr = pinned(depth), pinned(pose7), pinned(intr4)
-    h_boxes, h_wh, h_off = pinned(boxes), pinned(image_wh), pinned(frame_off)
-    h_out_t = torch.empty((nb, 24), dtype=torch.float32, pin_memory=True)
-    h_out = h_out_t.numpy().view(lift.RECORD_DTYPE).reshape(-1)
-    torch.cuda.synchronize()
-    h2d = sum(t.numel() * t.element_size() for t in (h_depth, h_pose, h_intr, h_boxes, h_wh, h_off))
-    d2h = nb * 96
-
-    def e2e_step():
-        lift.lift_boxes_host(
-            h_depth.numpy(), h_pose.numpy(), h_intr.numpy(), h_boxes.numpy(), h_wh.numpy(), h_off.numpy(),
-            device=local, out=h_out,
-        )
-
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    e2e_value = frames_total / e2e_s
-    # the host entry and the device entry must agree byte for byte (same deterministic kernels)
-    dev_rec = lift.records_to_numpy(plan.records[:nb])
-    e2e_match = bool(dev_rec.tobytes() == h_out.tobytes())
-
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, lift, (depth, pose7, intr4, boxes, image_wh, frame_off), nb, local, barrier,
+                      max_over_ranks, frames_total, plan)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------
@@ -406,7 +420,7 @@ def run_lm3d(args):
             "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": f"{WORKLOAD}: {F} frames x {H}x{W} fp32 depth, {B} boxes/frame per GPU "
+                "workload": f"{workload}: {F} frames x {H}x{W} fp32 depth, {B} boxes/frame per GPU "
                             f"(SURVEY 8d law, generated in HBM)",
                 "frames_per_gpu": F,
                 "boxes_per_gpu": nb,
@@ -415,15 +429,7 @@ def run_lm3d(args):
             },
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "e2e": {
-                "value": e2e_value,
-                "unit": UNIT,
-                "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "api": "lm3d_lift_boxes_host (pinned host buffers, chunked H2D overlapped with compute)",
-                "steps": e2e_steps,
-                "matches_device_path": e2e_match,
-            },
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -440,6 +446,9 @@ def main():
     ap.add_argument("--impl", default="lm3d", choices=["lm3d", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="override frames per GPU (debug only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["C1", "C2", "C3", "C5"],
+                    help="diagnostics: another BASELINE config shape (use with --frames; the driver never passes this)")
+    ap.add_argument("--no-e2e", action="store_true", help="diagnostics: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

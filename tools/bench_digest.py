@@ -11,6 +11,6 @@ for ln in open(sys.argv[1]):
     print(
         f"value={d['value']:.4g} {d['unit']} ms/step={d['ms_per_step']:.4g} frac={r.get('frac', 0):.4f} "
         f"kernel_ms={ {k: round(v, 4) for k, v in (r.get('kernel_ms') or {}).items()} } "
-        f"e2e={d['e2e']['value']:.4g} match={d['e2e'].get('matches_device_path')} "
+        f"e2e={(d.get('e2e') or {}).get('value')} match={(d.get('e2e') or {}).get('matches_device_path')} "
         f"cpu={(d.get('cpu_baseline') or {}).get('value')} rare={r.get('rare_paths')}"
     )
