@@ -345,4 +345,54 @@ __device__ __forceinline__ void write_record(float* __restrict__ outw, float* __
   for (int i = 0; i < 6; ++i) o4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
+// fp32 finalisation for warp boxes (<= 8160 pixels: fp32 sums of centred terms are exact to
+// ~1e-6 relative; the CTA kernel keeps the fp64 version above).
+__device__ __forceinline__ void write_record_f32(float* __restrict__ outw, float* __restrict__ ostats,
+                                                 const FrameTab& tb, int x0, int y0, int x1, int y1, float uc,
+                                                 float vc, float s0, float su, float sv, const float (&mn)[3],
+                                                 const float (&mx)[3], int n_valid, uint32_t k0, uint32_t k1,
+                                                 float gamma, float inv_scale) {
+  const int n_pix = (x1 - x0 + 1) * (y1 - y0 + 1);
+  float w[24];
+  const float qnan = __uint_as_float(0x7fc00000u);
+  if (n_valid <= 0) {
+#pragma unroll
+    for (int i = 0; i < 22; ++i) w[i] = qnan;
+    w[22] = __int_as_float(0);
+    w[23] = __int_as_float(n_pix);
+    if (ostats) { ostats[0] = qnan; ostats[1] = qnan; }
+  } else {
+    const float dlo = __uint_as_float(k0), dhi = __uint_as_float(k1);
+    const float diff = dhi - dlo;  // numpy _lerp, both branches
+    const float dq = (gamma >= 0.5f) ? dhi - diff * (1.0f - gamma) : dlo + diff * gamma;
+    const float fu[2] = {(float)x0, (float)x1}, fv[2] = {(float)y0, (float)y1};
+    const int cui[4] = {0, 0, 1, 1}, cvi[4] = {0, 1, 1, 0};
+    const float inv_n = 1.0f / (float)n_valid;
+    const float mean_d = s0 * inv_n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        w[c * 3 + k] = fmaf(dq, fmaf(tb.a[k], fu[cui[c]], fmaf(tb.b[k], fv[cvi[c]], tb.c[k])), tb.t[k]);
+      const float gc = fmaf(tb.a[k], uc, fmaf(tb.b[k], vc, tb.c[k]));  // ray term at the rect centre
+      w[12 + k] = fmaf(gc, mean_d, fmaf(tb.a[k] * inv_n, su, fmaf(tb.b[k] * inv_n, sv, tb.t[k])));
+      w[15 + k] = mn[k] + tb.t[k];
+      w[18 + k] = mx[k] + tb.t[k];
+    }
+    w[21] = dq * inv_scale;
+    w[22] = __int_as_float(n_valid);
+    w[23] = __int_as_float(n_pix);
+    if (ostats) { ostats[0] = dlo; ostats[1] = dhi; }
+  }
+  float4* o4 = reinterpret_cast<float4*>(outw);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
 }  // namespace lm3d

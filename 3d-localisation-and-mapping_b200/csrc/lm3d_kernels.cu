@@ -417,7 +417,7 @@ __device__ __forceinline__ void small_sample_bracket(const float* __restrict__ f
   lo = 1u;
   hi = kKeyMaxValid;
   if (n_pix <= 32) return;
-  if (n_pix <= 3072) sample_bracket_regs<2>(fbase, W, rc, dmax_bits, quant, kBracketZ, lane, lo, hi);
+  if (n_pix <= 1024) sample_bracket_regs<2>(fbase, W, rc, dmax_bits, quant, kBracketZ, lane, lo, hi);
   else if (n_pix <= 6144) sample_bracket_regs<4>(fbase, W, rc, dmax_bits, quant, 2.5f, lane, lo, hi);
   else sample_bracket_smem(fbase, W, rc, dmax_bits, quant, 2.5f, lane, smp, lo, hi);
 }
@@ -434,10 +434,10 @@ struct Acc {
 // as a float it is a NaN (dropped by FMNMX3), as a key it is above every bracket.
 // Keys inside the bracket are appended to the warp's dense candidate array (ballot + popc
 // compaction: no atomics, no per-lane imbalance).
-__device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint32_t dmaxA, uint32_t dmaxB, f32x2 vr2,
+__device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint32_t dmax, f32x2 vr2,
                                            f32x2 b0, f32x2 b1, f32x2 b2, f32x2 c0, f32x2 c1, f32x2 c2, uint32_t lo,
                                            uint32_t span, Acc& A, uint32_t cand_s, uint32_t lt_mask, int& ncand) {
-  const bool vA = key_valid(bitsA, dmaxA), vB = key_valid(bitsB, dmaxB);
+  const bool vA = key_valid(bitsA, dmax), vB = key_valid(bitsB, dmax);
   const uint32_t keyA = vA ? bitsA : 0x7fffffffu, keyB = vB ? bitsB : 0x7fffffffu;
   const f32x2 dn = pack2(__uint_as_float(keyA), __uint_as_float(keyB));
   float xa, xb;
@@ -460,14 +460,17 @@ __device__ __forceinline__ void accum_pair(uint32_t bitsA, uint32_t bitsB, uint3
 }
 
 #ifndef LM3D_SMALL_MINB
-#define LM3D_SMALL_MINB 2
+#define LM3D_SMALL_MINB 3  // 24 warps/SM (80 registers): measured 2.15 ms vs 2.44 ms at 16 warps/SM on C2
 #endif
 __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_kernel(const LiftArgs A) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* cand = smem_u32 + wib * kSmallCap;
-  const uint32_t cand_s = (uint32_t)__cvta_generic_to_shared(cand);
-  const uint32_t lt_mask = lanemask_lt();
+  uint32_t cand_s, lt_mask;
+  // opaque moves: keep these two in registers (ptxas otherwise re-derives them from %tid / %lanemask
+  // inside the pixel loop when registers are tight -- 6 extra instructions per candidate push)
+  asm volatile("mov.u32 %0, %1;" : "=r"(cand_s) : "r"((uint32_t)__cvta_generic_to_shared(cand)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(lt_mask) : "r"(lanemask_lt()));
   const int n_items = A.counters[A.count_idx];
   const int W = A.W;
   const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
@@ -482,8 +485,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
     for (int item = item0; item < item1; ++item) {
       const int4* ip = reinterpret_cast<const int4*>(items + item);
       const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
-      const float4 t0 = __ldg(reinterpret_cast<const float4*>(ip + 2)), t1 = __ldg(reinterpret_cast<const float4*>(ip + 3)),
-                   t2 = __ldg(reinterpret_cast<const float4*>(ip + 4));
+      const float4* tp = reinterpret_cast<const float4*>(ip + 2);  // the frame table rides in the item (L1-resident)
       const int b = i0.x, f = i0.y;
       Rect rc;
       rc.x0 = i0.z; rc.y0 = i0.w; rc.x1 = i1.x; rc.y1 = i1.y;
@@ -495,11 +497,6 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
       if (b < 0 || f < 0 || rc.x0 < 0 || rc.y0 < 0 || rc.x1 >= W || rc.y1 >= A.H || rc.w < 1 || rc.h < 1)
         dbg_report(10, item, b, f);
 #endif
-      FrameTab tb;
-      tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
-      tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
-      tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
-
       // ---- sample -> bracket -------------------------------------------------------------
       uint32_t lo, hi;
       small_sample_bracket(fbase, W, rc, n_pix, A.dmax_bits, A.quant, lane, cand, lo, hi);
@@ -515,7 +512,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
       const uint32_t span = hi - lo;
       int ncand = 0, c_in_done = 0;  // warp-uniform: keys in the dense array / keys dropped by overflow resets
       bool overflow = false;
-      const f32x2 b0 = pack2(tb.b[0], tb.b[0]), b1 = pack2(tb.b[1], tb.b[1]), b2 = pack2(tb.b[2], tb.b[2]);
+      float tb_b0, tb_b1, tb_b2;
+      {
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        tb_b0 = t0.w; tb_b1 = t1.x; tb_b2 = t1.y;
+      }
+      const f32x2 b0 = pack2(tb_b0, tb_b0), b1 = pack2(tb_b1, tb_b1), b2 = pack2(tb_b2, tb_b2);
       const int RP = lm.RP;
       const uint32_t rpw = (uint32_t)(RP * W);
       const int k_full = rc.h / RP;                 // row steps every lane can take
@@ -527,68 +529,67 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
         const uint32_t dmax_lane = col_ok ? A.dmax_bits : 0u;  // idle lanes read column 0 and drop it
         const float uf = (float)(rc.x0 + cx);
         // column term of the ray, with the row centring folded in: a_k*u + c_k + b_k*vc
-        const float ck0 = fmaf(tb.b[0], vc, fmaf(tb.a[0], uf, tb.c[0]));
-        const float ck1 = fmaf(tb.b[1], vc, fmaf(tb.a[1], uf, tb.c[1]));
-        const float ck2 = fmaf(tb.b[2], vc, fmaf(tb.a[2], uf, tb.c[2]));
+        float ck0, ck1, ck2;
+        {  // a_k, c_k are only needed here: re-read them instead of holding 6 registers across the pass
+          const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+          ck0 = fmaf(tb_b0, vc, fmaf(t0.x, uf, t1.z));
+          ck1 = fmaf(tb_b1, vc, fmaf(t0.y, uf, t1.w));
+          ck2 = fmaf(tb_b2, vc, fmaf(t0.z, uf, t2.x));
+        }
         const f32x2 c0 = pack2(ck0, ck0), c1 = pack2(ck1, ck1), c2 = pack2(ck2, ck2);
         const uint32_t off_safe = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx : 0));  // row 0 of the lane's column
         uint32_t off = off_safe + (uint32_t)(lm.lr * W);
         const float vr0 = (float)(rc.y0 + lm.lr) - vc;
-        f32x2 vrA = pack2(vr0, vr0 + (float)RP), vrB = pack2(vr0 + (float)(2 * RP), vr0 + (float)(3 * RP));
+        f32x2 vrA = pack2(vr0, vr0 + (float)RP);
+        const f32x2 step2 = pack2((float)(2 * RP), (float)(2 * RP));
         acc.s0 = 0.f;
 #pragma unroll 1
         for (int k = 0; k < k_all; k += 4) {
-          uint32_t q[4], dm[4];
+          uint32_t q[4];
           if (k + 4 <= k_full) {  // warp-uniform: every lane owns all four rows of this group
             const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
             q[0] = __float_as_uint(LM3D_LDG(fbase, off, hw_lim, 1, item, k));
             q[1] = __float_as_uint(LM3D_LDG(fbase, o1, hw_lim, 2, item, k));
             q[2] = __float_as_uint(LM3D_LDG(fbase, o2, hw_lim, 3, item, k));
             q[3] = __float_as_uint(LM3D_LDG(fbase, o3, hw_lim, 4, item, k));
-            dm[0] = dm[1] = dm[2] = dm[3] = dmax_lane;
-          } else {  // ragged tail: clamp the row, mask by validity ceiling
+          } else {  // ragged tail: rows below the rect are not read and count as invalid (bits 0)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int ry = (k + j) * RP + lm.lr;
-              const bool ok = ry < rc.h;
-              dm[j] = ok ? dmax_lane : 0u;
-              const uint32_t oj = ok ? off + (uint32_t)j * rpw : off_safe;  // never touch rows below the rect
-              q[j] = __float_as_uint(LM3D_LDG(fbase, oj, hw_lim, 5, item, k));
+              q[j] = 0u;
+              if (ry < rc.h) q[j] = __float_as_uint(LM3D_LDG(fbase, off + (uint32_t)j * rpw, hw_lim, 5, item, k));
             }
           }
           if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }  // uniform, rare
-          accum_pair(q[0], q[1], dm[0], dm[1], vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
-          accum_pair(q[2], q[3], dm[2], dm[3], vrB, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
+          accum_pair(q[0], q[1], dmax_lane, vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
+          accum_pair(q[2], q[3], dmax_lane, add2(vrA, step2), b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
           off += 4 * rpw;
           vrA = add2(vrA, step4);
-          vrB = add2(vrB, step4);
         }
         su = fmaf(uf - uc, acc.s0, su);
         s0_all += acc.s0;
       }
 
       // ---- warp reduction ----------------------------------------------------------------
-      BoxSums S;
-      S.n_valid = warp_sum_i((int)acc.n_valid);
+      const int n_valid_box = warp_sum_i((int)acc.n_valid);
       const int c_lt = warp_sum_i(acc.c_lt);
       const int c_in = c_in_done + ncand;
       __syncwarp();
-      S.s0 = warp_sum_d((double)s0_all);
-      S.su = warp_sum_d((double)su);
-      S.sv = warp_sum_d((double)acc.sv);
-      S.mn[0] = warp_min_f(acc.mn0); S.mn[1] = warp_min_f(acc.mn1); S.mn[2] = warp_min_f(acc.mn2);
-      S.mx[0] = warp_max_f(acc.mx0); S.mx[1] = warp_max_f(acc.mx1); S.mx[2] = warp_max_f(acc.mx2);
+      const float S0 = warp_sum_f(s0_all), SU = warp_sum_f(su), SV = warp_sum_f(acc.sv);
+      float mn[3], mx[3];
+      mn[0] = warp_min_f(acc.mn0); mn[1] = warp_min_f(acc.mn1); mn[2] = warp_min_f(acc.mn2);
+      mx[0] = warp_max_f(acc.mx0); mx[1] = warp_max_f(acc.mx1); mx[2] = warp_max_f(acc.mx2);
 
       // ---- exact order statistics --------------------------------------------------------
       uint32_t k0 = 0, k1 = 0;
       double gamma = 0.0;
-      if (S.n_valid > 0) {
+      if (n_valid_box > 0) {
         int r; bool two;
-        order_ranks(S.n_valid, A.quant, r, two, gamma);
+        order_ranks(n_valid_box, A.quant, r, two, gamma);
         {
           const int rhi = r + (two ? 1 : 0);
           SelWindow win;
-          win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = S.n_valid;
+          win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = n_valid_box;
           win.straddle = false; win.split = 0u;
           bool done = false;
           if (overflow && lane == 0) atomicAdd(&A.counters[6], 1);
@@ -599,13 +600,20 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
               done = true;
             }
           } else if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
-          else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below = c_lt + c_in; win.cnt = S.n_valid - win.below; }
+          else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below = c_lt + c_in; win.cnt = n_valid_box - win.below; }
           if (!done) warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, win, r, two, A.counters, k0, k1);
         }
       }
-      if (lane == 0)
-        write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
-                     tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
+      if (lane == 0) {
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        FrameTab tb;
+        tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
+        tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
+        tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+        write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
+                         tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
+                         (float)(1.0 / A.scale_depth));
+      }
       __syncwarp();
     }
     item_next = __shfl_sync(kFull, item_next, 0);
