@@ -56,3 +56,34 @@ def gather_counts(n_local: int, device, group=None) -> list[int]:
     out = torch.empty((world,), dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(out, t, group=group)
     return [int(v) for v in out.cpu()]
+
+
+class PipelinedGather:
+    """Overlap the record all-gather of step ``i`` with the lift of step ``i+1``.
+
+    The gather runs on the process group's own stream (``async_op=True``) into one of two
+    output buffers; the caller alternates two ``LiftPlan`` record buffers the same way and calls
+    ``ready(slot)`` before reusing a slot.  At 8 GPUs the gather of a C2 shard (19.2 MB out,
+    134 MB in per rank) costs ~0.3 ms against ~2 ms of lift, so hiding it is what takes the
+    weak-scaling efficiency from 6.9x to the compute-only figure."""
+
+    def __init__(self, n_records: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.out = [torch.empty((self.world * n_records, 24), dtype=torch.float32, device=device) for _ in range(2)]
+        self.pending = [None, None]
+
+    def ready(self, slot: int):
+        """Make the current stream wait until the gather that last used ``slot`` has finished."""
+        if self.pending[slot] is not None:
+            self.pending[slot].wait()
+            self.pending[slot] = None
+
+    def launch(self, slot: int, records: torch.Tensor):
+        if self.world == 1:
+            return
+        self.pending[slot] = dist.all_gather_into_tensor(self.out[slot], records, group=self.group, async_op=True)
+
+    def drain(self):
+        for s in (0, 1):
+            self.ready(s)
