@@ -389,6 +389,40 @@ __device__ __forceinline__ void write_record_f32(float* __restrict__ outw, float
   for (int i = 0; i < 6; ++i) o4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// mbarrier + TMA (cp.async.bulk.tensor, SASS UTMALDG) helpers for the per-warp tile ring.
+// Measured on B200: a tiled TMA load faults ("illegal instruction") unless the innermost
+// start coordinate is 16-byte aligned, so tiles start at x0 & ~3.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar_s, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nLM3D_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LM3D_DONE_%=;\nbra LM3D_WAIT_%=;\nLM3D_DONE_%=:\n}" ::"r"(bar_s), "r"(parity)
+      : "memory");
+}
+// 3-D tile (x, y, frame) of the depth tensor -> shared memory; completes `bytes` on the mbarrier
+__device__ __forceinline__ void tma_load_tile_3d(uint32_t dst_s, const void* tensor_map, uint32_t bar_s, int x, int y,
+                                                 int f) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst_s),
+      "l"((unsigned long long)tensor_map), "r"(bar_s), "r"(x), "r"(y), "r"(f)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr_s) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr_s));
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

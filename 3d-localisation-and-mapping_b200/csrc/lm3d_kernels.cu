@@ -12,6 +12,7 @@
 // pose transform + min/max/sum reduction AND the counting half of an exact percentile
 // select (sample -> bracket -> count/collect), followed by an exact finish on the few
 // collected candidates in shared memory.  No sort of the box, no global histogram.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -44,8 +45,10 @@ struct Workspace {
   FrameTab* tab;        // [F]
   int32_t* box_frame;   // [B]
   void* small_items;    // [B] WorkItem (80 B): everything a warp needs for one box, one load level
+  void* tma_items;      // [B] WorkItem: warp boxes that take the TMA-fed kernel
   int32_t* large_list;  // [B]
-  int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor
+  int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor, 4..6 rare-path stats,
+                        //       8 n_tma, 9 tma cursor
 };
 
 struct __align__(16) WorkItem {
@@ -67,12 +70,14 @@ static size_t workspace_layout(int64_t F, int64_t B, char* base, Workspace* ws) 
   char* t = take((size_t)F * sizeof(FrameTab));
   char* bf = take((size_t)B * 4);
   char* sl = take((size_t)B * 80);
+  char* tl = take((size_t)B * 80);
   char* ll = take((size_t)B * 4);
   if (ws) {
     ws->counters = (int32_t*)c;
     ws->tab = (FrameTab*)t;
     ws->box_frame = (int32_t*)bf;
     ws->small_items = (void*)sl;
+    ws->tma_items = (void*)tl;
     ws->large_list = (int32_t*)ll;
   }
   return off;
@@ -122,10 +127,11 @@ __device__ __forceinline__ int64_t csr_find(const int64_t* __restrict__ off, int
 __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64_t* __restrict__ frame_off,
                                   int64_t F, int64_t B, int H, int W, const FrameTab* __restrict__ tab,
                                   int32_t* __restrict__ box_frame, WorkItem* __restrict__ small_items,
+                                  WorkItem* __restrict__ tma_items, int tma_max_span,
                                   int32_t* __restrict__ large_list, int32_t* __restrict__ counters) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  bool is_small = false, is_large = false;
+  bool is_small = false, is_large = false, is_tma = false;
   int f = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   if (b < B) {
     f = (int)csr_find(frame_off, F, b);
@@ -137,19 +143,26 @@ __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64
     const int64_t area = (int64_t)(x1 - x0 + 1) * (y1 - y0 + 1);
     is_small = area <= kSmallMaxPix;
     is_large = !is_small;
+    // TMA-fed warp kernel: the tile (16-byte aligned start column .. x1) must fit one tensor-map class
+    is_tma = is_small && ((x0 & 3) + (x1 - x0 + 1) <= tma_max_span);
+    is_small = is_small && !is_tma;
   }
   // warp-aggregated, order-preserving append (keeps frame locality in the lists)
   const uint32_t ms = __ballot_sync(kFull, is_small), ml = __ballot_sync(kFull, is_large);
-  int bs = 0, bl = 0;
+  const uint32_t mt = __ballot_sync(kFull, is_tma);
+  int bs = 0, bl = 0, bt = 0;
   if (lane == 0) {
     if (ms) bs = atomicAdd(&counters[0], __popc(ms));
     if (ml) bl = atomicAdd(&counters[1], __popc(ml));
+    if (mt) bt = atomicAdd(&counters[8], __popc(mt));
   }
   bs = __shfl_sync(kFull, bs, 0);
   bl = __shfl_sync(kFull, bl, 0);
+  bt = __shfl_sync(kFull, bt, 0);
   const uint32_t lt = lanemask_lt();
-  if (is_small) {
-    int4* dst = reinterpret_cast<int4*>(small_items + bs + __popc(ms & lt));
+  if (is_small || is_tma) {
+    int4* dst = is_tma ? reinterpret_cast<int4*>(tma_items + bt + __popc(mt & lt))
+                       : reinterpret_cast<int4*>(small_items + bs + __popc(ms & lt));
     const float4* tp = reinterpret_cast<const float4*>(tab + f);
     dst[0] = make_int4((int)b, f, x0, y0);
     dst[1] = make_int4(x1, y1, 0, 0);
@@ -621,6 +634,318 @@ __global__ void __launch_bounds__(kSmallWarps * 32, LM3D_SMALL_MINB) lift_small_
 }
 
 // ------------------------------------------------------------------------------------------
+// 3b. small boxes, TMA-fed: one warp per box, pixels streamed through a per-warp ring of
+//     shared-memory tiles by the TMA unit (cp.async.bulk.tensor, 3-D tensor map over
+//     [F,H,W]); the warp never issues a global load for pixel data.
+// ------------------------------------------------------------------------------------------
+// A box is cut into row chunks; chunk c is ONE tensor-map tile of tw x th floats
+// (tw = 16*cls covers the rect columns from the 16-byte aligned start x0 & ~3, th = kTmaChunk/tw
+// rows), at most kTmaChunk floats.  The tile stream of a warp runs ahead of its arithmetic by
+// kTmaNS-1 tiles and crosses box boundaries (the next box is claimed one box early), so DRAM
+// latency is covered by the ring rather than by resident warps.  Out-of-frame tile elements
+// are zero-filled by the TMA unit (zero = invalid depth); in-frame elements outside the rect
+// are masked by lane (columns) and by the row loop bounds.
+constexpr int kTmaNS = 2;              // ring slots per warp (measured: 2 already feeds 11 TB/s of tiles)
+constexpr int kTmaChunk = 1024;        // floats per slot (4 KB)
+constexpr int kTmaClasses = 16;        // tile widths 16, 32, ..., 256
+#ifndef LM3D_TMA_WARPS
+#define LM3D_TMA_WARPS 14
+#endif
+constexpr int kTmaWarps = LM3D_TMA_WARPS;
+constexpr size_t kTmaSmemBytes = (size_t)kTmaWarps * (kTmaNS * kTmaChunk * 4 + kSmallCap * 4) + kTmaWarps * kTmaNS * 8;
+
+struct TileMaps {
+  CUtensorMap m[kTmaClasses];
+};
+
+struct BoxGeo {
+  int b, f, x0, y0, w, h;  // h == 0: no box
+};
+__device__ __forceinline__ BoxGeo geo_from_item(const int4 i0, const int4 i1) {
+  BoxGeo g;
+  g.b = i0.x; g.f = i0.y; g.x0 = i0.z; g.y0 = i0.w;
+  g.w = i1.x - i0.z + 1; g.h = i1.y - i0.w + 1;
+  return g;
+}
+__device__ __forceinline__ int geo_cls(const BoxGeo& g) { return ((g.x0 & 3) + g.w + 15) >> 4; }  // 1..kTmaClasses
+__device__ __forceinline__ int cls_rows(int cls) { return (kTmaChunk / 16) / cls; }
+
+// prefetched lattice sample of a box (same lattice as sample_bracket_regs)
+__device__ __forceinline__ void sample_load(const float* __restrict__ depth, size_t HW, int W, const BoxGeo& g, int lane,
+                                            uint32_t (&s)[4]) {
+  const int n_pix = g.w * g.h;
+  s[0] = s[1] = s[2] = s[3] = 0u;
+  if (g.h == 0 || n_pix <= 32 || n_pix > 6144) return;
+  const float* fbase = depth + (size_t)g.f * HW;
+  const int E = (n_pix <= 1024) ? 2 : 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (e < E) {
+      const int i = e * 32 + lane;
+      const int ic = i & 7, ir = i >> 3;
+      const int cx = ((2 * ic + 1) * g.w) >> 4;
+      const int ry = ((2 * ir + 1) * g.h) / (8 * E);
+      s[e] = __float_as_uint(__ldg(fbase + (uint32_t)((g.y0 + ry) * W + g.x0 + cx)));
+    }
+  }
+}
+template <int E>
+__device__ __forceinline__ void bracket_from_sample(const uint32_t (&raw)[4], uint32_t dmax_bits, double quant, float z,
+                                                    int lane, uint32_t& lo, uint32_t& hi) {
+  uint32_t s[E];
+  int sv = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool v = key_valid(raw[e], dmax_bits);
+    s[e] = v ? raw[e] : kKeyInvalid;
+    sv += v;
+  }
+  sv = warp_sum_i(sv);
+  if (sv == 0) return;
+  warp_bitonic<E>(s, lane);
+  int a, b;
+  bracket_ranks(sv, quant, z, a, b);
+  const uint32_t sa = warp_sorted_at<E>(s, max(a, 0));
+  const uint32_t sb = warp_sorted_at<E>(s, min(max(b, 0), 32 * E - 1));
+  if (a >= 0) lo = sa;
+  if (b < sv) hi = sb;
+}
+
+__global__ void __launch_bounds__(kTmaWarps * 32, 1) lift_tma_kernel(const __grid_constant__ TileMaps maps, const LiftArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t ring_s = smem_s + (uint32_t)wib * (kTmaNS * kTmaChunk * 4);
+  uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTmaWarps * kTmaNS * kTmaChunk * 4) + wib * kSmallCap;
+  const uint32_t bar_s = smem_s + (uint32_t)(kTmaWarps * (kTmaNS * kTmaChunk * 4 + kSmallCap * 4)) + (uint32_t)wib * (kTmaNS * 8);
+  uint32_t cand_s, lt_mask;
+  asm volatile("mov.u32 %0, %1;" : "=r"(cand_s) : "r"((uint32_t)__cvta_generic_to_shared(cand)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(lt_mask) : "r"(lanemask_lt()));
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaNS; ++s) mbar_init(bar_s + 8 * s, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const int n_items = A.counters[A.count_idx];
+  const int W = A.W;
+  const size_t HW = (size_t)A.H * W;
+  const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
+
+  // ---- work pipeline: cur (being reduced) / nxt (tiles may already be in flight) / nn (geometry
+  //      loading) / pend (claim in flight) ----------------------------------------------------
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&A.counters[A.cursor_idx], 3);
+  base = __shfl_sync(kFull, base, 0);
+  int idx_cur = base, idx_nxt = base + 1, idx_nn = base + 2;
+  int pend = 0;
+  if (lane == 0) pend = atomicAdd(&A.counters[A.cursor_idx], 1);
+  BoxGeo cur, nxt;
+  cur.h = nxt.h = 0; cur.w = nxt.w = 1; cur.b = cur.f = cur.x0 = cur.y0 = 0; nxt.b = nxt.f = nxt.x0 = nxt.y0 = 0;
+  int4 nn0 = make_int4(0, 0, 0, 0), nn1 = make_int4(0, -1, 0, 0);
+  float4 tc0, tc1, tc2, tn0, tn1, tn2;  // frame tables of cur / nxt
+  tc0 = tc1 = tc2 = tn0 = tn1 = tn2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx_cur < n_items) {
+    const int4* ip = reinterpret_cast<const int4*>(items + idx_cur);
+    cur = geo_from_item(__ldg(ip), __ldg(ip + 1));
+    const float4* tp = reinterpret_cast<const float4*>(ip + 2);
+    tc0 = __ldg(tp); tc1 = __ldg(tp + 1); tc2 = __ldg(tp + 2);
+  }
+  if (idx_nxt < n_items) {
+    const int4* ip = reinterpret_cast<const int4*>(items + idx_nxt);
+    nxt = geo_from_item(__ldg(ip), __ldg(ip + 1));
+    const float4* tp = reinterpret_cast<const float4*>(ip + 2);
+    tn0 = __ldg(tp); tn1 = __ldg(tp + 1); tn2 = __ldg(tp + 2);
+  }
+  if (idx_nn < n_items) {
+    const int4* ip = reinterpret_cast<const int4*>(items + idx_nn);
+    nn0 = __ldg(ip); nn1 = __ldg(ip + 1);
+  }
+  uint32_t smp_cur[4], smp_nxt[4];
+  sample_load(A.depth, HW, W, cur, lane, smp_cur);
+  sample_load(A.depth, HW, W, nxt, lane, smp_nxt);
+
+  // ---- tile stream (producer side; only lane 0 talks to the TMA unit) -------------------------
+  int pg = 0, prow = 0;       // next tile to issue: rows prow.. of box (pg == 0 ? cur : nxt); pg == 2: both issued
+  int in_flight = 0;          // tiles issued and not yet consumed
+  int pslot = 0, cslot = 0;   // ring positions of the next issue / next consume
+  uint32_t cphase = 0u;       // bit s = parity the consumer waits for on slot s
+  auto try_issue = [&]() {
+    if (in_flight >= kTmaNS || pg >= 2) return;
+    // by-value selects (a reference to cur/nxt would force both into local memory)
+    const int gx0 = pg ? nxt.x0 : cur.x0, gy0 = pg ? nxt.y0 : cur.y0, gw = pg ? nxt.w : cur.w, gh = pg ? nxt.h : cur.h,
+              gf = pg ? nxt.f : cur.f;
+    if (gh == 0) return;
+    const int cls = ((gx0 & 3) + gw + 15) >> 4;
+    const int th = cls_rows(cls);
+    if (lane == 0) {
+      mbar_expect_tx(bar_s + 8 * pslot, (uint32_t)(cls * 16 * th * 4));
+      tma_load_tile_3d(ring_s + (uint32_t)pslot * (kTmaChunk * 4), &maps.m[cls - 1], bar_s + 8 * pslot, gx0 & ~3,
+                       gy0 + prow, gf);
+    }
+    ++in_flight;
+    pslot = (pslot + 1 == kTmaNS) ? 0 : pslot + 1;
+    prow += th;
+    if (prow >= gh) { prow = 0; ++pg; }
+  };
+#pragma unroll
+  for (int s = 0; s < kTmaNS; ++s) try_issue();
+
+  while (cur.h != 0) {
+    const int n_pix = cur.w * cur.h;
+    const float* __restrict__ fbase = A.depth + (size_t)cur.f * HW;
+    Rect rc;
+    rc.x0 = cur.x0; rc.y0 = cur.y0; rc.w = cur.w; rc.h = cur.h; rc.x1 = cur.x0 + cur.w - 1; rc.y1 = cur.y0 + cur.h - 1;
+
+    // ---- bracket from the prefetched sample --------------------------------------------------
+    uint32_t lo = 1u, hi = kKeyMaxValid;
+    if (n_pix > 32) {
+      if (n_pix <= 1024) bracket_from_sample<2>(smp_cur, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
+      else if (n_pix <= 6144) bracket_from_sample<4>(smp_cur, A.dmax_bits, A.quant, 2.5f, lane, lo, hi);
+      else sample_bracket_smem(fbase, W, rc, A.dmax_bits, A.quant, 2.5f, lane, cand, lo, hi);
+    }
+
+    // ---- fused pass over the tiles of this box -------------------------------------------------
+    const LaneMap lm = lane_map(cur.w, lane);
+    const int RP = lm.RP;
+    const int cls = geo_cls(cur);
+    const int tw = cls * 16, th = cls_rows(cls);
+    const int xoff = cur.x0 & 3;
+    const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+    Acc acc;
+    acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
+    acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
+    acc.s0 = 0.f; acc.sv = 0.f; acc.n_valid = 0.f; acc.c_lt = 0;
+    float s0_all = 0.f, su = 0.f;
+    const uint32_t span = hi - lo;
+    int ncand = 0, c_in_done = 0;
+    bool overflow = false;
+    const f32x2 b0 = pack2(tc0.w, tc0.w), b1 = pack2(tc1.x, tc1.x), b2 = pack2(tc1.y, tc1.y);
+    const uint32_t rpw = (uint32_t)(RP * tw * 4);  // bytes between two row steps of a lane
+    const f32x2 step4 = pack2((float)(4 * RP), (float)(4 * RP));
+    const f32x2 step2 = pack2((float)(2 * RP), (float)(2 * RP));
+
+    for (int r0 = 0; r0 < cur.h; r0 += th) {
+      const int nr = min(th, cur.h - r0);
+      const int k_full = nr / RP;
+      const int k_all = (nr + RP - 1) / RP;
+      mbar_wait(bar_s + 8 * cslot, (cphase >> cslot) & 1u);
+      const uint32_t tile_s = ring_s + (uint32_t)cslot * (kTmaChunk * 4);
+      for (int cx0 = 0; cx0 < cur.w; cx0 += lm.G) {
+        const int cx = cx0 + lm.lc;
+        const bool col_ok = cx < cur.w;
+        const uint32_t dmax_lane = col_ok ? A.dmax_bits : 0u;  // idle lanes read column 0 and drop it
+        const float uf = (float)(cur.x0 + cx);
+        const float ck0 = fmaf(tc0.w, vc, fmaf(tc0.x, uf, tc1.z));
+        const float ck1 = fmaf(tc1.x, vc, fmaf(tc0.y, uf, tc1.w));
+        const float ck2 = fmaf(tc1.y, vc, fmaf(tc0.z, uf, tc2.x));
+        const f32x2 c0 = pack2(ck0, ck0), c1 = pack2(ck1, ck1), c2 = pack2(ck2, ck2);
+        uint32_t off = tile_s + (uint32_t)((lm.lr * tw + xoff + (col_ok ? cx : 0)) * 4);
+        const float vr0 = (float)(cur.y0 + r0 + lm.lr) - vc;
+        f32x2 vrA = pack2(vr0, vr0 + (float)RP);
+        acc.s0 = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < k_all; k += 4) {
+          uint32_t q[4];
+          if (k + 4 <= k_full) {  // warp-uniform: every lane owns all four rows of this group
+            q[0] = lds_u32(off);
+            q[1] = lds_u32(off + rpw);
+            q[2] = lds_u32(off + 2 * rpw);
+            q[3] = lds_u32(off + 3 * rpw);
+          } else {  // ragged tail: rows below the chunk / rect are not read and count as invalid (bits 0)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ry = (k + j) * RP + lm.lr;
+              q[j] = 0u;
+              if (ry < nr) q[j] = lds_u32(off + (uint32_t)j * rpw);
+            }
+          }
+          if (ncand > kSmallCap - 128) { overflow = true; c_in_done += ncand; ncand = 0; }  // uniform, rare
+          accum_pair(q[0], q[1], dmax_lane, vrA, b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
+          accum_pair(q[2], q[3], dmax_lane, add2(vrA, step2), b0, b1, b2, c0, c1, c2, lo, span, acc, cand_s, lt_mask, ncand);
+          off += 4 * rpw;
+          vrA = add2(vrA, step4);
+        }
+        su = fmaf(uf - uc, acc.s0, su);
+        s0_all += acc.s0;
+      }
+      __syncwarp();  // every lane is done with the slot before it is handed back to the TMA unit
+      --in_flight;
+      cphase ^= 1u << cslot;
+      cslot = (cslot + 1 == kTmaNS) ? 0 : cslot + 1;
+      try_issue();
+    }
+
+    // ---- warp reduction ------------------------------------------------------------------------
+    const int n_valid_box = warp_sum_i((int)acc.n_valid);
+    const int c_lt = warp_sum_i(acc.c_lt);
+    const int c_in = c_in_done + ncand;
+    __syncwarp();
+    const float S0 = warp_sum_f(s0_all), SU = warp_sum_f(su), SV = warp_sum_f(acc.sv);
+    float mn[3], mx[3];
+    mn[0] = warp_min_f(acc.mn0); mn[1] = warp_min_f(acc.mn1); mn[2] = warp_min_f(acc.mn2);
+    mx[0] = warp_max_f(acc.mx0); mx[1] = warp_max_f(acc.mx1); mx[2] = warp_max_f(acc.mx2);
+
+    // ---- exact order statistics ----------------------------------------------------------------
+    uint32_t k0 = 0, k1 = 0;
+    double gamma = 0.0;
+    if (n_valid_box > 0) {
+      int r; bool two;
+      order_ranks(n_valid_box, A.quant, r, two, gamma);
+      const int rhi = r + (two ? 1 : 0);
+      SelWindow win;
+      win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = n_valid_box;
+      win.straddle = false; win.split = 0u;
+      bool done = false;
+      if (overflow && lane == 0) atomicAdd(&A.counters[6], 1);
+      if (r >= c_lt && rhi < c_lt + c_in) {
+        win.wlo = lo; win.whi = hi; win.below = c_lt; win.cnt = c_in;
+        if (!overflow) {
+          warp_select_hist(cand, c_in, r - c_lt, two, lane, lo, hi, k0, k1);
+          done = true;
+        }
+      } else if (rhi < c_lt) { win.whi = lo - 1u; win.cnt = c_lt; }
+      else if (r >= c_lt + c_in) { win.wlo = hi + 1u; win.below = c_lt + c_in; win.cnt = n_valid_box - win.below; }
+      if (!done) warp_select_global(fbase, W, rc, A.dmax_bits, lane, cand, win, r, two, A.counters, k0, k1);
+    }
+    if (lane == 0) {
+      FrameTab tb;
+      tb.a[0] = tc0.x; tb.a[1] = tc0.y; tb.a[2] = tc0.z; tb.b[0] = tc0.w;
+      tb.b[1] = tc1.x; tb.b[2] = tc1.y; tb.c[0] = tc1.z; tb.c[1] = tc1.w;
+      tb.c[2] = tc2.x; tb.t[0] = tc2.y; tb.t[1] = tc2.z; tb.t[2] = tc2.w;
+      write_record_f32(reinterpret_cast<float*>(A.out + cur.b), A.order_stats ? A.order_stats + 2 * (size_t)cur.b : nullptr,
+                       tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
+                       (float)(1.0 / A.scale_depth));
+    }
+    __syncwarp();
+
+    // ---- shift the work pipeline -----------------------------------------------------------------
+    cur = nxt;
+    tc0 = tn0; tc1 = tn1; tc2 = tn2;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) smp_cur[e] = smp_nxt[e];
+    pg = max(pg - 1, 0);  // pg was >= 1: every tile of the finished box had been issued
+    idx_nxt = idx_nn;
+    nxt.h = 0;
+    if (idx_nxt < n_items) {
+      nxt = geo_from_item(nn0, nn1);
+      const float4* tp = reinterpret_cast<const float4*>(reinterpret_cast<const int4*>(items + idx_nxt) + 2);
+      tn0 = __ldg(tp); tn1 = __ldg(tp + 1); tn2 = __ldg(tp + 2);
+    }
+    idx_nn = __shfl_sync(kFull, pend, 0);
+    if (idx_nn < n_items) {
+      const int4* ip = reinterpret_cast<const int4*>(items + idx_nn);
+      nn0 = __ldg(ip); nn1 = __ldg(ip + 1);
+      if (lane == 0) pend = atomicAdd(&A.counters[A.cursor_idx], 1);
+    }
+    sample_load(A.depth, HW, W, nxt, lane, smp_nxt);
+#pragma unroll
+    for (int s = 0; s < kTmaNS; ++s) try_issue();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 4. large boxes: one CTA per box
 // ------------------------------------------------------------------------------------------
 struct LargeShared {
@@ -979,10 +1304,11 @@ __global__ void __launch_bounds__(256) frame_cloud_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------
 static std::atomic<int64_t> g_launches{0};
 
-// Optional per-kernel timing of lm3d_lift_boxes (bench.py's roofline leg): when enabled, five
-// events bracket the four kernels on the caller's stream.  Not thread-safe; off by default.
+// Optional per-kernel timing of lm3d_lift_boxes (bench.py's roofline leg): when enabled, six
+// events bracket the five kernels on the caller's stream.  Not thread-safe; off by default.
+constexpr int kProfKernels = 5;
 static bool g_profile = false;
-static cudaEvent_t g_prof_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static cudaEvent_t g_prof_ev[kProfKernels + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 static bool g_prof_valid = false;
 static inline void prof_mark(int i, cudaStream_t st) {
   if (g_profile) cudaEventRecord(g_prof_ev[i], st);
@@ -990,7 +1316,7 @@ static inline void prof_mark(int i, cudaStream_t st) {
 
 struct DeviceInfo {
   int sms = 0;
-  int small_ctas = 1, large_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
+  int small_ctas = 1, large_ctas = 1, tma_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
   bool ok = false;
   bool attrs_set = false;
 };
@@ -1022,12 +1348,61 @@ static int device_info(DeviceInfo** out) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.large_ctas, lift_large_kernel, kLargeThreads,
                                                       (kLargeCap + kSortCap) * 4);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(lift_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tma_ctas, lift_tma_kernel, kTmaWarps * 32, kTmaSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    d.tma_ctas = std::max(d.tma_ctas, 1);
     d.small_ctas = std::max(d.small_ctas, 1);
     d.large_ctas = std::max(d.large_ctas, 1);
     d.attrs_set = true;
   }
   *out = &d;
   return LM3D_OK;
+}
+
+
+// Tensor maps of the TMA-fed kernel: one 3-D map over depth[F,H,W] per tile class (tile width
+// 16*cls floats, kTmaChunk/(16*cls) rows, 1 frame), no swizzle, zero fill outside the tensor.
+// cuTensorMapEncodeTiled is a host-only encoder; it is resolved through the runtime so that
+// liblm3d.so has no link-time dependency on libcuda.  Returns the widest usable tile span in
+// floats (0: TMA path unusable for this tensor, the legacy warp kernel takes every small box).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static bool g_encode_tried = false;
+static bool g_tma_disabled = false;
+
+static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, TileMaps* maps) {
+  if (!g_encode_tried) {
+    g_encode_tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode_tiled = (EncodeTiledFn)fn;
+  }
+  memset(maps, 0, sizeof(TileMaps));
+  const char* env = getenv("LM3D_NO_TMA");  // A/B switch for tests and benchmarks: force the direct-load warp kernel
+  g_tma_disabled = env && env[0] == '1';
+  if (!g_encode_tiled || g_tma_disabled) return 0;
+  if ((W & 3) != 0 || (((uintptr_t)depth) & 15) != 0) return 0;  // global strides must be multiples of 16 bytes
+  int span = 0;
+  for (int cls = 1; cls <= kTmaClasses; ++cls) {
+    const int tw = 16 * cls, th = (kTmaChunk / 16) / cls;
+    if (tw - 16 >= W + 3) break;  // no rect of this tensor needs a wider tile
+    cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
+    cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode_tiled(&maps->m[cls - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)depth, gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) break;
+    span = tw;
+  }
+  return span;
 }
 
 static uint32_t dmax_to_bits(double max_depth_mm) {
@@ -1074,7 +1449,7 @@ int lm3d_debug_read(int* out16) {
 
 int lm3d_profile_enable(int on) {
   if (on && !g_prof_ev[0]) {
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i <= kProfKernels; ++i) {
       cudaError_t e = cudaEventCreate(&g_prof_ev[i]);
       if (e != cudaSuccess) return (int)e;
     }
@@ -1084,12 +1459,12 @@ int lm3d_profile_enable(int on) {
   return LM3D_OK;
 }
 
-int lm3d_profile_read(float* ms4) {
-  if (!ms4 || !g_prof_valid) return LM3D_ERR_BAD_ARG;
-  cudaError_t e = cudaEventSynchronize(g_prof_ev[4]);
+int lm3d_profile_read(float* ms5) {
+  if (!ms5 || !g_prof_valid) return LM3D_ERR_BAD_ARG;
+  cudaError_t e = cudaEventSynchronize(g_prof_ev[kProfKernels]);
   if (e != cudaSuccess) return (int)e;
-  for (int i = 0; i < 4; ++i) {
-    e = cudaEventElapsedTime(&ms4[i], g_prof_ev[i], g_prof_ev[i + 1]);
+  for (int i = 0; i < kProfKernels; ++i) {
+    e = cudaEventElapsedTime(&ms5[i], g_prof_ev[i], g_prof_ev[i + 1]);
     if (e != cudaSuccess) return (int)e;
   }
   return LM3D_OK;
@@ -1143,8 +1518,11 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1001;
 #endif
   prof_mark(1, st);
+  TileMaps maps;
+  const int tma_span = build_tile_maps(depth, F, H, W, &maps);
   prep_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, frame_off, F, B, H, W, ws.tab, ws.box_frame,
-                                                               (WorkItem*)ws.small_items, ws.large_list, ws.counters);
+                                                               (WorkItem*)ws.small_items, (WorkItem*)ws.tma_items, tma_span,
+                                                               ws.large_list, ws.counters);
 #ifdef LM3D_DEBUG_BOUNDS
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1002;
 #endif
@@ -1158,16 +1536,28 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   A.out = out; A.order_stats = order_stats;
 
   // persistent grids: a multiple of the SM count, capped by the amount of work
-  {
+  if (tma_span > 0) {
+    A.list = nullptr; A.items = ws.tma_items; A.count_idx = 8; A.cursor_idx = 9;
+    const int64_t want = (B + kTmaWarps - 1) / kTmaWarps;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->tma_ctas));
+    lift_tma_kernel<<<grid, kTmaWarps * 32, kTmaSmemBytes, st>>>(maps, A);
+    g_launches += 1;
+  }
+#ifdef LM3D_DEBUG_BOUNDS
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1005;
+#endif
+  prof_mark(3, st);
+  if (tma_span < W) {  // otherwise every warp box fits a tile class and the legacy list is provably empty
     A.list = nullptr; A.items = ws.small_items; A.count_idx = 0; A.cursor_idx = 2;
     const int64_t want = (B + (int64_t)kSmallWarps * kSmallChunk - 1) / ((int64_t)kSmallWarps * kSmallChunk);
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->small_ctas));
     lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
+    g_launches += 1;
   }
 #ifdef LM3D_DEBUG_BOUNDS
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1003;
 #endif
-  prof_mark(3, st);
+  prof_mark(4, st);
   {
     A.list = ws.large_list; A.items = nullptr; A.count_idx = 1; A.cursor_idx = 3;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)dev->sms * dev->large_ctas));
@@ -1176,9 +1566,9 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
 #ifdef LM3D_DEBUG_BOUNDS
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1004;
 #endif
-  prof_mark(4, st);
+  prof_mark(5, st);
   g_prof_valid = g_profile;
-  g_launches += 4;
+  g_launches += 3;
   return (int)cudaGetLastError();
 }
 

@@ -352,8 +352,8 @@ def run_lm3d(args):
     lib.lm3d_profile_enable(1)
     import ctypes
 
-    ms4 = (ctypes.c_float * 4)()
-    kern = np.zeros(4)
+    ms4 = (ctypes.c_float * 5)()
+    kern = np.zeros(5)
     reps = max(3, min(args.steps, 10))
     for _ in range(reps):
         lift.lift_boxes(depth, pose7, intr4, rect4, frame_off, plan=plan)
@@ -368,7 +368,7 @@ def run_lm3d(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dom = 2 if kern[2] >= kern[3] else 3
+    dom = 2 + int(np.argmax(kern[2:5]))
     achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -379,7 +379,7 @@ def run_lm3d(args):
             traffic = None
     roofline = {
         "bound": "hbm",
-        "kernel": ["prep_frames_kernel", "prep_boxes_kernel", "lift_small_kernel", "lift_large_kernel"][dom],
+        "kernel": ["prep_frames_kernel", "prep_boxes_kernel", "lift_tma_kernel", "lift_small_kernel", "lift_large_kernel"][dom],
         "achieved": achieved,
         "peak": peak,
         "peak_source": peak_src,
@@ -387,7 +387,8 @@ def run_lm3d(args):
         "frac": achieved / peak,
         "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes,
-        "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_small": kern[2], "lift_large": kern[3]},
+        "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_tma": kern[2], "lift_small": kern[3],
+                      "lift_large": kern[4]},
         "rare_paths": {"global_fallbacks": rare[0], "narrowing_passes": rare[1], "candidate_overflows": rare[2]},
     }
 

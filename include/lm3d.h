@@ -110,11 +110,13 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
 int64_t lm3d_kernel_launches(void);
 
 /* Measurement hooks (bench.py's roofline leg; not part of the data path, not thread-safe).
- * While enabled, lm3d_lift_boxes brackets its four kernels with CUDA events on the caller's
- * stream; lm3d_profile_read waits for the last call and returns the four durations in ms:
- * [0] frame table, [1] box prep, [2] warp-per-box lift, [3] CTA-per-box lift. */
+ * While enabled, lm3d_lift_boxes brackets its five kernels with CUDA events on the caller's
+ * stream; lm3d_profile_read waits for the last call and returns the five durations in ms:
+ * [0] frame table, [1] box prep, [2] warp-per-box lift fed by TMA tiles, [3] warp-per-box
+ * lift with direct loads (rects no tensor-map tile class fits, or W % 4 != 0; not launched
+ * when no rect can need it), [4] CTA-per-box lift. */
 int lm3d_profile_enable(int on);
-int lm3d_profile_read(float* ms4);
+int lm3d_profile_read(float* ms5);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,14 @@ from parity import assert_records_match
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["tma", "direct"])
+def warp_kernel_path(request, monkeypatch):
+    """Every parity case runs twice: warp boxes through the TMA-fed kernel (default) and through the
+    direct-load warp kernel (LM3D_NO_TMA=1, also what W % 4 != 0 tensors take)."""
+    monkeypatch.setenv("LM3D_NO_TMA", "1" if request.param == "direct" else "0")
+    return request.param
+
+
 def run_cuda(seq, dev, rect4=None, q=50.0, max_depth_mm=float("inf")):
     from lm3d import lift
 
@@ -98,6 +106,40 @@ def test_edge_rects(cuda_device):
     ]
     _rect_case(cuda_device, depth, rects)
     _rect_case(cuda_device, depth, rects, q=25.0)
+
+
+def test_tile_classes_and_alignment(cuda_device):
+    """TMA tiles start at x0 & ~3 and come in 16-column classes: sweep start phases, widths around the
+    class boundaries, chunk-boundary heights, frame edges (zero-filled tile elements) and several frames."""
+    rng = np.random.default_rng(8)
+    depth = (900 + 700 * rng.random((3, 256, 192))).astype(np.float32)
+    depth[rng.random(depth.shape) < 0.03] = 0.0
+    rects = []
+    for f in range(3):
+        per = []
+        for x0 in (0, 1, 2, 3, 61):
+            for w in (1, 13, 16, 17, 29, 31, 32, 33, 47, 48, 49, 77, 80):
+                if x0 + w <= 192:
+                    per.append((x0, 5 + f, x0 + w - 1, 5 + f + [1, 20, 21, 22, 43, 64, 97][(x0 + w) % 7] - 1))
+        per += [(0, 250, 191, 255), (1, 0, 190, 40), (129, 200, 191, 255), (188, 0, 191, 255), (0, 0, 3, 255),
+                (2, 100, 5, 227), (96, 128, 191, 200)]
+        rects += per
+    n = len(rects) // 3
+    _rect_case(cuda_device, depth, rects[:n] + rects[n:2 * n] + rects[2 * n:3 * n])
+    _rect_case(cuda_device, depth, rects[:n] + rects[n:2 * n] + rects[2 * n:3 * n], q=90.0)
+
+
+def test_widths_not_multiple_of_16_or_4(cuda_device):
+    """W = 100 (tile classes wider than the frame are never needed) and W = 50 (global stride not a
+    multiple of 16 bytes: the tensor map cannot be built, the direct-load kernel takes every box)."""
+    rng = np.random.default_rng(9)
+    for W in (100, 50):
+        depth = (900 + 700 * rng.random((2, 64, W))).astype(np.float32)
+        rects = []
+        for f in range(2):
+            rects += [(0, 0, W - 1, 63), (1, 2, W - 2, 30), (W - 7, 10, W - 1, 60), (3, 3, 3, 3), (5, 0, 40, 63),
+                      (W // 2, 1, W - 1, 9)]
+        _rect_case(cuda_device, depth, rects)
 
 
 def test_ties_and_constant_planes(cuda_device):
