@@ -402,12 +402,17 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
 }
+// Bounded: a tile that never lands (a producer/consumer bookkeeping bug) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nLM3D_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra LM3D_DONE_%=;\nbra LM3D_WAIT_%=;\nLM3D_DONE_%=:\n}" ::"r"(bar_s), "r"(parity)
-      : "memory");
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_s), "r"(parity)
+        : "memory");
+    if (spins > (1u << 20)) __trap();
+  }
 }
 // 3-D tile (x, y, frame) of the depth tensor -> shared memory; completes `bytes` on the mbarrier
 __device__ __forceinline__ void tma_load_tile_3d(uint32_t dst_s, const void* tensor_map, uint32_t bar_s, int x, int y,
