@@ -428,6 +428,24 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr_s) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------
+// cp.async (LDGSTS) helpers: a lane streams its own 16-byte quads global -> shared several
+// row steps ahead of its arithmetic; src_bytes == 0 zero-fills (rows past the rect).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(uint32_t dst_s, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_s), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr_s) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr_s));
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

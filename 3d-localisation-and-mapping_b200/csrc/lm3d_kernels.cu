@@ -667,7 +667,7 @@ constexpr int kTmaClasses = 16;        // tile widths 16, 32, ..., 256
 constexpr int kHistWords = 320;        // 32 lane-private 'below' words, 256 bracket bins, 32 lane-private 'above' words;
                                        // reused as the dense key list after the scan
 constexpr int kCollCap = 256;          // keys pass 2 may collect
-constexpr int kCollRows = 16;          // private column depth per lane (+4 guard rows: one unclamped group of 4 appends)
+constexpr int kCollRows = 28;          // private column depth per lane (+4 guard rows: one unclamped group of 4 appends)
 constexpr int kCollWords = 32 * (kCollRows + 4);
 #ifndef LM3D_TMA_WARPS
 #define LM3D_TMA_WARPS 16
@@ -1141,6 +1141,610 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) lift_tma_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------
+// 3c. small boxes, direct loads + histogram percentile: one warp per box, 24 warps / SM.
+//     Same arithmetic as 3b (pass 1 = fused reduction + 256-bin bracket histogram, pass 2 =
+//     collect the keys of the bins holding the target ranks), but the pixels come through
+//     LDG (pass 2 re-reads the rect from L1/L2) and latency is covered by resident warps.
+//     Takes every warp box (no tile-class or alignment limits).
+// ------------------------------------------------------------------------------------------
+constexpr int kHistWarps = 8;
+constexpr int kHistWarpWords = kHistWords + kCollWords;
+#ifndef LM3D_HIST_MINB
+#define LM3D_HIST_MINB 3
+#endif
+
+__global__ void __launch_bounds__(kHistWarps * 32, LM3D_HIST_MINB) lift_hist_kernel(const LiftArgs A) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* hist = smem_u32 + wib * kHistWarpWords;
+  const uint32_t* coll = hist + kHistWords;
+  uint32_t hist_s, coll_s, lt_mask;
+  asm volatile("mov.u32 %0, %1;" : "=r"(hist_s) : "r"((uint32_t)__cvta_generic_to_shared(hist)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(coll_s) : "r"((uint32_t)__cvta_generic_to_shared(hist + kHistWords) + (uint32_t)lane * 4));
+  asm volatile("mov.u32 %0, %1;" : "=r"(lt_mask) : "r"(lanemask_lt()));
+  const int n_items = A.counters[A.count_idx];
+  const int W = A.W;
+  const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
+
+  int item_next = 0;
+  if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);
+  item_next = __shfl_sync(kFull, item_next, 0);
+  while (item_next < n_items) {
+    const int item0 = item_next;
+    const int item1 = min(item0 + kSmallChunk, n_items);
+    if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);  // claimed early, used late
+    for (int item = item0; item < item1; ++item) {
+      const int4* ip = reinterpret_cast<const int4*>(items + item);
+      const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+      const float4* tp = reinterpret_cast<const float4*>(ip + 2);  // the frame table rides in the item (L1-resident)
+      const int b = i0.x, f = i0.y;
+      Rect rc;
+      rc.x0 = i0.z; rc.y0 = i0.w; rc.x1 = i1.x; rc.y1 = i1.y;
+      rc.w = rc.x1 - rc.x0 + 1; rc.h = rc.y1 - rc.y0 + 1;
+      const int n_pix = rc.w * rc.h;
+      const float* __restrict__ fbase = A.depth + (size_t)f * A.H * W;
+
+      // ---- sample -> bracket -> histogram map ------------------------------------------------
+      uint32_t lo = 1u, hi = kKeyMaxValid;
+      if (n_pix > 64) sample_bracket_regs<2>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
+      hi = min(hi, A.dmax_bits);
+      float s4f, kkf;
+      {
+        const float lo_f = __uint_as_float(lo), hi_f = __uint_as_float(max(hi, 1u));
+        const float wd = hi_f - lo_f;
+        s4f = (wd > 0.f) ? fminf(1000.f / wd, 2097152.f / hi_f) : 0.f;
+        kkf = fmaf(-lo_f, s4f, 33554432.f + 4.f * 35.f);
+      }
+      const float ylo = 33554432.f + 4.f * (float)lane, yhi = 33554432.f + 4.f * (float)(288 + lane);
+      const uint32_t hist_bias = hist_s - 0x30000000u;
+#pragma unroll
+      for (int i = 0; i < kHistWords / 32; ++i) hist[i * 32 + lane] = 0u;
+      __syncwarp();
+
+      // ---- pass 1: unproject + pose + reduce + histogram ----------------------------------------
+      const LaneMap lm = lane_map(rc.w, lane);
+      const int RP = lm.RP;
+      const uint32_t rpw = (uint32_t)(RP * W);
+      const int k_full = rc.h / RP;
+      const int k_all = (rc.h + RP - 1) / RP;
+      const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+      Acc2 acc;
+      acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
+      acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
+      acc.s0 = 0.f; acc.sv = 0.f; acc.n_valid = 0.f;
+      float s0_all = 0.f, su = 0.f;
+      {
+        float tb_b0, tb_b1, tb_b2;
+        {
+          const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+          tb_b0 = t0.w; tb_b1 = t1.x; tb_b2 = t1.y;
+        }
+        const f32x2 b0 = pack2(tb_b0, tb_b0), b1 = pack2(tb_b1, tb_b1), b2 = pack2(tb_b2, tb_b2);
+        const f32x2 s4 = pack2(s4f, s4f), kk = pack2(kkf, kkf);
+        const f32x2 step4 = pack2((float)(4 * RP), (float)(4 * RP));
+        const f32x2 step2 = pack2((float)(2 * RP), (float)(2 * RP));
+        for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
+          const int cx = cx0 + lm.lc;
+          const bool col_ok = cx < rc.w;
+          const uint32_t dmax_lane = col_ok ? A.dmax_bits : 0u;  // idle lanes read column 0 and drop it
+          const float uf = (float)(rc.x0 + cx);
+          float ck0, ck1, ck2;
+          {  // a_k, c_k are only needed here: re-read them instead of holding 6 registers across the pass
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            ck0 = fmaf(tb_b0, vc, fmaf(t0.x, uf, t1.z));
+            ck1 = fmaf(tb_b1, vc, fmaf(t0.y, uf, t1.w));
+            ck2 = fmaf(tb_b2, vc, fmaf(t0.z, uf, t2.x));
+          }
+          const f32x2 c0 = pack2(ck0, ck0), c1 = pack2(ck1, ck1), c2 = pack2(ck2, ck2);
+          uint32_t off = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx : 0)) + (uint32_t)(lm.lr * W);
+          const float vr0 = (float)(rc.y0 + lm.lr) - vc;
+          f32x2 vrA = pack2(vr0, vr0 + (float)RP);
+          acc.s0 = 0.f;
+          int k = 0;
+#pragma unroll 1
+          for (; k + 4 <= k_full; k += 4) {
+            const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
+            const uint32_t q0 = __float_as_uint(__ldg(fbase + off)), q1 = __float_as_uint(__ldg(fbase + o1)),
+                           q2 = __float_as_uint(__ldg(fbase + o2)), q3 = __float_as_uint(__ldg(fbase + o3));
+            accum_pair_hist(q0, q1, dmax_lane, vrA, b0, b1, b2, c0, c1, c2, s4, kk, ylo, yhi, hist_bias, acc);
+            accum_pair_hist(q2, q3, dmax_lane, add2(vrA, step2), b0, b1, b2, c0, c1, c2, s4, kk, ylo, yhi, hist_bias, acc);
+            off += 4 * rpw;
+            vrA = add2(vrA, step4);
+          }
+#pragma unroll 1
+          for (; k < k_all; k += 2) {  // ragged tail: rows below the rect are not read and count as invalid (bits 0)
+            const int ryA = k * RP + lm.lr, ryB = ryA + RP;
+            const uint32_t q0 = (ryA < rc.h) ? __float_as_uint(__ldg(fbase + off)) : 0u,
+                           q1 = (ryB < rc.h) ? __float_as_uint(__ldg(fbase + off + rpw)) : 0u;
+            accum_pair_hist(q0, q1, dmax_lane, vrA, b0, b1, b2, c0, c1, c2, s4, kk, ylo, yhi, hist_bias, acc);
+            off += 2 * rpw;
+            vrA = add2(vrA, step2);
+          }
+          su = fmaf(uf - uc, acc.s0, su);
+          s0_all += acc.s0;
+        }
+      }
+
+      // ---- warp reduction ----------------------------------------------------------------
+      const int n_valid_box = warp_sum_i((int)acc.n_valid);
+      const float S0 = warp_sum_f(s0_all), SU = warp_sum_f(su), SV = warp_sum_f(acc.sv);
+      float mn[3], mx[3];
+      mn[0] = warp_min_f(acc.mn0); mn[1] = warp_min_f(acc.mn1); mn[2] = warp_min_f(acc.mn2);
+      mx[0] = warp_max_f(acc.mx0); mx[1] = warp_max_f(acc.mx1); mx[2] = warp_max_f(acc.mx2);
+
+      // ---- which bins hold the target ranks? ----------------------------------------------------
+      int r = 0; bool two = false; double gamma = 0.0;
+      if (n_valid_box > 0) order_ranks(n_valid_box, A.quant, r, two, gamma);
+      const int r1 = r + (two ? 1 : 0);
+      __syncwarp();
+      int b_lo = -1, b_hi = -1, before = 0, n_coll = 0;
+      {
+        const int below_all = warp_sum_i((int)hist[lane]), above = warp_sum_i((int)hist[288 + lane]);
+        const uint4 h0 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane], h1 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane + 1];
+        const int c[8] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += c[i];
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int in_all = __shfl_sync(kFull, incl, 31);
+        const int below = below_all - (below_all + in_all + above - n_valid_box);
+        int cum = below + incl - tot;
+        int my_lo = -1, my_hi = -1, my_before = 0, my_end = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r >= cum && r < cum + c[i]) { my_lo = 32 + lane * 8 + i; my_before = cum; }
+          if (r1 >= cum && r1 < cum + c[i]) { my_hi = 32 + lane * 8 + i; my_end = cum + c[i]; }
+          cum += c[i];
+        }
+        const uint32_t m_lo = __ballot_sync(kFull, my_lo >= 0), m_hi = __ballot_sync(kFull, my_hi >= 0);
+        if (n_valid_box > 0 && m_lo && m_hi) {
+          b_lo = __shfl_sync(kFull, my_lo, __ffs(m_lo) - 1);
+          before = __shfl_sync(kFull, my_before, __ffs(m_lo) - 1);
+          b_hi = __shfl_sync(kFull, my_hi, __ffs(m_hi) - 1);
+          n_coll = __shfl_sync(kFull, my_end, __ffs(m_hi) - 1) - before;
+        }
+      }
+      const bool collect = (b_lo >= 32) && (n_coll <= kCollCap);
+      const uint32_t tgt = 0x4C000000u + (uint32_t)max(b_lo, 0), dt = collect ? (uint32_t)(b_hi - b_lo) : 0u;
+
+      // ---- pass 2: re-read the rect (L1 / L2), keep the keys of the target bins in private columns ----
+      uint32_t cptr = coll_s;
+      const uint32_t cend = coll_s + kCollRows * 128;
+      if (collect) {
+        for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
+          const bool col_ok = cx0 + lm.lc < rc.w;
+          const uint32_t tgt_lane = col_ok ? tgt : 0xffffff00u;  // idle lanes match nothing
+          uint32_t off = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx0 + lm.lc : 0)) + (uint32_t)(lm.lr * W);
+          int k = 0;
+#pragma unroll 1
+          for (; k + 4 <= k_full; k += 4) {
+            const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
+            const uint32_t q0 = __float_as_uint(__ldg(fbase + off)), q1 = __float_as_uint(__ldg(fbase + o1)),
+                           q2 = __float_as_uint(__ldg(fbase + o2)), q3 = __float_as_uint(__ldg(fbase + o3));
+            collect_px(q0, s4f, kkf, tgt_lane, dt, cptr);
+            collect_px(q1, s4f, kkf, tgt_lane, dt, cptr);
+            collect_px(q2, s4f, kkf, tgt_lane, dt, cptr);
+            collect_px(q3, s4f, kkf, tgt_lane, dt, cptr);
+            cptr = min(cptr, cend);
+            off += 4 * rpw;
+          }
+#pragma unroll 1
+          for (; k < k_all; ++k) {
+            const int ry = k * RP + lm.lr;
+            if (ry < rc.h) collect_px(__float_as_uint(__ldg(fbase + off)), s4f, kkf, tgt_lane, dt, cptr);
+            cptr = min(cptr, cend);
+            off += rpw;
+          }
+        }
+      }
+
+      // ---- exact order statistics ----------------------------------------------------------------
+      uint32_t k0 = 0, k1 = 0;
+      if (n_valid_box > 0) {
+        __syncwarp();
+        bool done = false;
+        if (collect && !__any_sync(kFull, cptr >= cend)) {
+          const int cnt_l = (int)((cptr - coll_s) >> 7);
+          const int rows = (int)warp_max_u((uint32_t)cnt_l);
+          int ncoll = 0;
+          for (int row = 0; row < rows; ++row) {
+            const uint32_t key = (row < cnt_l) ? coll[row * 32 + lane] : 0u;
+            const bool in = key_valid(key, A.dmax_bits);
+            const uint32_t bal = __ballot_sync(kFull, in);
+            const int pos = ncoll + __popc(bal & lt_mask);
+            if (in && pos < kCollCap) hist[pos] = key;
+            ncoll += __popc(bal);
+          }
+          __syncwarp();
+          if (ncoll == n_coll) {
+            const int rl = r - before;
+            if (ncoll <= 32) {
+              uint32_t s1[1] = {(lane < ncoll) ? hist[lane] : kKeyInvalid};
+              warp_bitonic<1>(s1, lane);
+              k0 = __shfl_sync(kFull, s1[0], rl);
+              k1 = two ? __shfl_sync(kFull, s1[0], rl + 1) : k0;
+            } else {
+              uint32_t kmn = kKeyInvalid, kmx = 0u;
+              for (int i = lane; i < ncoll; i += 32) { kmn = min(kmn, hist[i]); kmx = max(kmx, hist[i]); }
+              kmn = warp_min_u(kmn); kmx = warp_max_u(kmx);
+              warp_select_hist(hist, ncoll, rl, two, lane, kmn, kmx, k0, k1);
+            }
+            done = true;
+          }
+        }
+        if (!done) {
+          SelWindow win;
+          win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = n_valid_box;
+          win.straddle = false; win.split = 0u;
+          warp_select_global(fbase, W, rc, A.dmax_bits, lane, hist, kCollCap, win, r, two, A.counters, k0, k1);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        FrameTab tb;
+        tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
+        tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
+        tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+        write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
+                         tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
+                         (float)(1.0 / A.scale_depth));
+      }
+      __syncwarp();
+    }
+    item_next = __shfl_sync(kFull, item_next, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3d. small boxes, float4 loads: one warp per box, a lane owns FOUR consecutive pixels of a row.
+//     One LDG.128 per lane and row step (16-byte aligned: the quads start at x0 & ~3), so a
+//     rect <= 64 px wide needs no column passes at all, the loads per pixel drop 4x and the
+//     bytes in flight per warp rise 4x -- the direct-load kernels above are bound by load
+//     latency (ncu: 53 % of the stall samples are long-scoreboard waits on first use).
+//     Same two-pass histogram percentile as 3b / 3c.  Needs W % 4 == 0.
+// ------------------------------------------------------------------------------------------
+constexpr int kQuadWarps = 8;
+#ifndef LM3D_QUAD_MINB
+#define LM3D_QUAD_MINB 3
+#endif
+#ifndef LM3D_QUAD_DEPTH
+#define LM3D_QUAD_DEPTH 4
+#endif
+constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight (cp.async groups)
+constexpr int kQuadWarpWords = kHistWarpWords + kQuadDepth * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
+
+struct AccQ {
+  float mn0, mn1, mn2, mx0, mx1, mx2;
+  float s0[4];     // per-column sum of valid depths (the column offsets are lane constants)
+  float sv, n_valid;
+};
+
+// pass 1 on one quad (4 pixels of one row, columns col0 .. col0+3)
+__device__ __forceinline__ void accum_quad_hist(const uint4 q, const uint32_t (&dm)[4], float vr, float b0, float b1, float b2,
+                                                const f32x2 (&cA)[3], const f32x2 (&cB)[3], float s4f, float kkf, float ylo,
+                                                float yhi, uint32_t hist_bias, AccQ& A) {
+  const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+  bool v[4];
+  uint32_t key[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = key_valid(bits[j], dm[j]);
+    key[j] = v[j] ? bits[j] : 0x7fffffffu;
+  }
+  const f32x2 dA = pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), dB = pack2(__uint_as_float(key[2]), __uint_as_float(key[3]));
+  const f32x2 vr2 = pack2(vr, vr);
+  float xa, xb;
+  f32x2 m;
+  m = mul2(dA, fma2(pack2(b0, b0), vr2, cA[0])); unpack2(m, xa, xb); A.mn0 = fmin3(A.mn0, xa, xb); A.mx0 = fmax3(A.mx0, xa, xb);
+  m = mul2(dB, fma2(pack2(b0, b0), vr2, cB[0])); unpack2(m, xa, xb); A.mn0 = fmin3(A.mn0, xa, xb); A.mx0 = fmax3(A.mx0, xa, xb);
+  m = mul2(dA, fma2(pack2(b1, b1), vr2, cA[1])); unpack2(m, xa, xb); A.mn1 = fmin3(A.mn1, xa, xb); A.mx1 = fmax3(A.mx1, xa, xb);
+  m = mul2(dB, fma2(pack2(b1, b1), vr2, cB[1])); unpack2(m, xa, xb); A.mn1 = fmin3(A.mn1, xa, xb); A.mx1 = fmax3(A.mx1, xa, xb);
+  m = mul2(dA, fma2(pack2(b2, b2), vr2, cA[2])); unpack2(m, xa, xb); A.mn2 = fmin3(A.mn2, xa, xb); A.mx2 = fmax3(A.mx2, xa, xb);
+  m = mul2(dB, fma2(pack2(b2, b2), vr2, cB[2])); unpack2(m, xa, xb); A.mn2 = fmin3(A.mn2, xa, xb); A.mx2 = fmax3(A.mx2, xa, xb);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (v[j]) { A.n_valid += 1.0f; A.s0[j] += __uint_as_float(bits[j]); A.sv = fmaf(vr, __uint_as_float(bits[j]), A.sv); }
+  float y[4];
+  unpack2(fma2(dA, pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+  unpack2(fma2(dB, pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float yc = fminf(fmaxf(y[j], ylo), yhi);  // NaN -> ylo
+    const uint32_t ad = __float_as_uint(yc) * 4u + hist_bias;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(ad) : "memory");
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_u4(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_kernel(const LiftArgs A) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* hist = smem_u32 + wib * kQuadWarpWords;
+  const uint32_t* coll = hist + kHistWords;
+  uint32_t hist_s, coll_s, pipe_s, lt_mask;
+  asm volatile("mov.u32 %0, %1;" : "=r"(hist_s) : "r"((uint32_t)__cvta_generic_to_shared(hist)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(coll_s) : "r"((uint32_t)__cvta_generic_to_shared(hist + kHistWords) + (uint32_t)lane * 4));
+  asm volatile("mov.u32 %0, %1;" : "=r"(pipe_s) : "r"((uint32_t)__cvta_generic_to_shared(hist + kHistWarpWords) + (uint32_t)lane * 16));
+  asm volatile("mov.u32 %0, %1;" : "=r"(lt_mask) : "r"(lanemask_lt()));
+  const int n_items = A.counters[A.count_idx];
+  const int W = A.W;
+  const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
+
+  int item_next = 0;
+  if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);
+  item_next = __shfl_sync(kFull, item_next, 0);
+  while (item_next < n_items) {
+    const int item0 = item_next;
+    const int item1 = min(item0 + kSmallChunk, n_items);
+    if (lane == 0) item_next = atomicAdd(&A.counters[A.cursor_idx], kSmallChunk);  // claimed early, used late
+    for (int item = item0; item < item1; ++item) {
+      const int4* ip = reinterpret_cast<const int4*>(items + item);
+      const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+      const float4* tp = reinterpret_cast<const float4*>(ip + 2);  // the frame table rides in the item (L1-resident)
+      const int b = i0.x, f = i0.y;
+      Rect rc;
+      rc.x0 = i0.z; rc.y0 = i0.w; rc.x1 = i1.x; rc.y1 = i1.y;
+      rc.w = rc.x1 - rc.x0 + 1; rc.h = rc.y1 - rc.y0 + 1;
+      const int n_pix = rc.w * rc.h;
+      const float* __restrict__ fbase = A.depth + (size_t)f * A.H * W;
+
+      // ---- sample -> bracket -> histogram map ------------------------------------------------
+      uint32_t lo = 1u, hi = kKeyMaxValid;
+      if (n_pix > 64) sample_bracket_regs<2>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
+      hi = min(hi, A.dmax_bits);
+      float s4f, kkf;
+      {
+        const float lo_f = __uint_as_float(lo), hi_f = __uint_as_float(max(hi, 1u));
+        const float wd = hi_f - lo_f;
+        s4f = (wd > 0.f) ? fminf(1000.f / wd, 2097152.f / hi_f) : 0.f;
+        kkf = fmaf(-lo_f, s4f, 33554432.f + 4.f * 35.f);
+      }
+      const float ylo = 33554432.f + 4.f * (float)lane, yhi = 33554432.f + 4.f * (float)(288 + lane);
+      const uint32_t hist_bias = hist_s - 0x30000000u;
+#pragma unroll
+      for (int i = 0; i < kHistWords / 32; ++i) hist[i * 32 + lane] = 0u;
+      __syncwarp();
+
+      // ---- quad geometry: Q quads per row from the aligned start, P column passes of Qp <= 16 quads,
+      //      RPq rows per step; lane -> (row r, quad q) --------------------------------------------------
+      const int xa = rc.x0 & ~3;
+      const int Q = (rc.x1 - xa + 4) >> 2;
+      // P column passes of Qp <= 16 quads, RPq = 32 / Qp rows per step: take the P (of three candidates) that
+      // covers the most rect rows per step and pass, e.g. Q = 12: P = 2, Qp = 6, RPq = 5 (30 lanes) beats P = 1 (24 lanes)
+      int P = (Q + 15) >> 4, Qp = (Q + P - 1) / P, RPq = 32 / Qp;
+#pragma unroll
+      for (int dp = 1; dp <= 2; ++dp) {
+        const int P2 = ((Q + 15) >> 4) + dp, Qp2 = (Q + P2 - 1) / P2, R2 = 32 / Qp2;
+        if (R2 * P > RPq * P2) { P = P2; Qp = Qp2; RPq = R2; }
+      }
+      const int lr = (lane * ((65536 + Qp - 1) / Qp)) >> 16;  // lane / Qp (exact for lane < 32)
+      const int lq = lane - lr * Qp;
+      const bool active = lr < RPq;
+      const int nsteps = (rc.h + RPq - 1) / RPq;
+      const uint32_t rstep = (uint32_t)(RPq * W);
+      const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+      const float frp = (float)RPq;
+
+      // ---- pass 1: unproject + pose + reduce + histogram ----------------------------------------
+      AccQ acc;
+      acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
+      acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
+      acc.sv = 0.f; acc.n_valid = 0.f;
+      float s0_all = 0.f, su = 0.f;
+      {
+        float tb_b0, tb_b1, tb_b2;
+        {
+          const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+          tb_b0 = t0.w; tb_b1 = t1.x; tb_b2 = t1.y;
+        }
+        for (int p = 0; p < P; ++p) {
+          const int qq = p * Qp + lq;
+          const bool lane_ok = active && qq < Q;
+          const int col0 = xa + 4 * (lane_ok ? qq : 0);  // idle lanes re-read quad 0 of row lr' = 0 and drop it
+          uint32_t dm[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dm[j] = (lane_ok && col0 + j >= rc.x0 && col0 + j <= rc.x1) ? A.dmax_bits : 0u;
+          f32x2 cA[3], cB[3];
+          {
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            const float uf = (float)col0;
+            const float ck0 = fmaf(tb_b0, vc, fmaf(t0.x, uf, t1.z));
+            const float ck1 = fmaf(tb_b1, vc, fmaf(t0.y, uf, t1.w));
+            const float ck2 = fmaf(tb_b2, vc, fmaf(t0.z, uf, t2.x));
+            cA[0] = pack2(ck0, ck0 + t0.x); cB[0] = pack2(fmaf(2.f, t0.x, ck0), fmaf(3.f, t0.x, ck0));
+            cA[1] = pack2(ck1, ck1 + t0.y); cB[1] = pack2(fmaf(2.f, t0.y, ck1), fmaf(3.f, t0.y, ck1));
+            cA[2] = pack2(ck2, ck2 + t0.z); cB[2] = pack2(fmaf(2.f, t0.z, ck2), fmaf(3.f, t0.z, ck2));
+          }
+          const int row_l = lane_ok ? lr : 0;
+          uint32_t off = (uint32_t)((rc.y0 + row_l) * W + col0);
+          float vr = (float)(rc.y0 + row_l) - vc;
+          acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
+          // cp.async pipeline: the lane's quad of row step st + kQuadDepth is requested before step st is reduced;
+          // steps past the rect (and the padding up to a multiple of kQuadDepth) arrive as zeros = invalid pixels
+          const float* gp = fbase + off;
+          const int rows_l = rc.h - row_l;  // this lane's row of step st is inside the rect iff st * RPq < rows_l
+#pragma unroll
+          for (int i = 0; i < kQuadDepth; ++i) {
+            cp_async_16(pipe_s + i * 512, gp, (i * RPq < rows_l) ? 16u : 0u);
+            cp_async_commit();
+            gp += rstep;
+          }
+          int nxt_row = kQuadDepth * RPq;  // row offset (relative to the lane's first row) of the next step to request
+#pragma unroll 1
+          for (int st = 0; st < nsteps; st += kQuadDepth) {
+#pragma unroll
+            for (int i = 0; i < kQuadDepth; ++i) {
+              cp_async_wait<kQuadDepth - 1>();
+              const uint4 q0 = lds_u4(pipe_s + i * 512);
+              cp_async_16(pipe_s + i * 512, gp, (nxt_row < rows_l) ? 16u : 0u);
+              cp_async_commit();
+              gp += rstep;
+              nxt_row += RPq;
+              accum_quad_hist(q0, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc);
+              vr += frp;
+            }
+          }
+          cp_async_wait<0>();  // drain the (zero-size) requests past the rect before the slots are reused
+          const float du = (float)col0 - uc;
+          su = fmaf(du, acc.s0[0], fmaf(du + 1.f, acc.s0[1], fmaf(du + 2.f, acc.s0[2], fmaf(du + 3.f, acc.s0[3], su))));
+          s0_all += (acc.s0[0] + acc.s0[1]) + (acc.s0[2] + acc.s0[3]);
+        }
+      }
+
+      // ---- warp reduction ----------------------------------------------------------------
+      const int n_valid_box = warp_sum_i((int)acc.n_valid);
+      const float S0 = warp_sum_f(s0_all), SU = warp_sum_f(su), SV = warp_sum_f(acc.sv);
+      float mn[3], mx[3];
+      mn[0] = warp_min_f(acc.mn0); mn[1] = warp_min_f(acc.mn1); mn[2] = warp_min_f(acc.mn2);
+      mx[0] = warp_max_f(acc.mx0); mx[1] = warp_max_f(acc.mx1); mx[2] = warp_max_f(acc.mx2);
+
+      // ---- which bins hold the target ranks? ----------------------------------------------------
+      int r = 0; bool two = false; double gamma = 0.0;
+      if (n_valid_box > 0) order_ranks(n_valid_box, A.quant, r, two, gamma);
+      const int r1 = r + (two ? 1 : 0);
+      __syncwarp();
+      int b_lo = -1, b_hi = -1, before = 0, n_coll = 0;
+      {
+        const int below_all = warp_sum_i((int)hist[lane]), above = warp_sum_i((int)hist[288 + lane]);
+        const uint4 h0 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane], h1 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane + 1];
+        const int c[8] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += c[i];
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int in_all = __shfl_sync(kFull, incl, 31);
+        const int below = below_all - (below_all + in_all + above - n_valid_box);
+        int cum = below + incl - tot;
+        int my_lo = -1, my_hi = -1, my_before = 0, my_end = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r >= cum && r < cum + c[i]) { my_lo = 32 + lane * 8 + i; my_before = cum; }
+          if (r1 >= cum && r1 < cum + c[i]) { my_hi = 32 + lane * 8 + i; my_end = cum + c[i]; }
+          cum += c[i];
+        }
+        const uint32_t m_lo = __ballot_sync(kFull, my_lo >= 0), m_hi = __ballot_sync(kFull, my_hi >= 0);
+        if (n_valid_box > 0 && m_lo && m_hi) {
+          b_lo = __shfl_sync(kFull, my_lo, __ffs(m_lo) - 1);
+          before = __shfl_sync(kFull, my_before, __ffs(m_lo) - 1);
+          b_hi = __shfl_sync(kFull, my_hi, __ffs(m_hi) - 1);
+          n_coll = __shfl_sync(kFull, my_end, __ffs(m_hi) - 1) - before;
+        }
+      }
+      const bool collect = (b_lo >= 32) && (n_coll <= kCollCap);
+      const uint32_t tgt = 0x4C000000u + (uint32_t)max(b_lo, 0), dt = collect ? (uint32_t)(b_hi - b_lo) : 0u;
+
+      // ---- pass 2: re-read the rect (L1 / L2), keep the keys of the target bins in private columns ----
+      uint32_t cptr = coll_s;
+      const uint32_t cend = coll_s + kCollRows * 128;
+      if (collect) {
+        for (int p = 0; p < P; ++p) {
+          const int qq = p * Qp + lq;
+          const bool lane_ok = active && qq < Q;
+          const int col0 = xa + 4 * (lane_ok ? qq : 0);
+          uint32_t tg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tg[j] = (lane_ok && col0 + j >= rc.x0 && col0 + j <= rc.x1) ? tgt : 0xffffff00u;
+          const int row_l = lane_ok ? lr : 0;
+          uint32_t off = (uint32_t)((rc.y0 + row_l) * W + col0);
+          const float* gp = fbase + off;
+          const int rows_l = rc.h - row_l;
+#pragma unroll
+          for (int i = 0; i < kQuadDepth; ++i) {
+            cp_async_16(pipe_s + i * 512, gp, (i * RPq < rows_l) ? 16u : 0u);
+            cp_async_commit();
+            gp += rstep;
+          }
+          int nxt_row = kQuadDepth * RPq;
+#pragma unroll 1
+          for (int st = 0; st < nsteps; st += kQuadDepth) {
+#pragma unroll
+            for (int i = 0; i < kQuadDepth; ++i) {
+              cp_async_wait<kQuadDepth - 1>();
+              const uint4 q0 = lds_u4(pipe_s + i * 512);
+              cp_async_16(pipe_s + i * 512, gp, (nxt_row < rows_l) ? 16u : 0u);
+              cp_async_commit();
+              gp += rstep;
+              nxt_row += RPq;
+              collect_px(q0.x, s4f, kkf, tg[0], dt, cptr); collect_px(q0.y, s4f, kkf, tg[1], dt, cptr);
+              collect_px(q0.z, s4f, kkf, tg[2], dt, cptr); collect_px(q0.w, s4f, kkf, tg[3], dt, cptr);
+              cptr = min(cptr, cend);
+            }
+          }
+          cp_async_wait<0>();
+        }
+      }
+
+      // ---- exact order statistics ----------------------------------------------------------------
+      uint32_t k0 = 0, k1 = 0;
+      if (n_valid_box > 0) {
+        __syncwarp();
+        bool done = false;
+        if (collect && !__any_sync(kFull, cptr >= cend)) {
+          const int cnt_l = (int)((cptr - coll_s) >> 7);
+          const int rows = (int)warp_max_u((uint32_t)cnt_l);
+          int ncoll = 0;
+          for (int row = 0; row < rows; ++row) {
+            const uint32_t key = (row < cnt_l) ? coll[row * 32 + lane] : 0u;
+            const bool in = key_valid(key, A.dmax_bits);
+            const uint32_t bal = __ballot_sync(kFull, in);
+            const int pos = ncoll + __popc(bal & lt_mask);
+            if (in && pos < kCollCap) hist[pos] = key;
+            ncoll += __popc(bal);
+          }
+          __syncwarp();
+          if (ncoll == n_coll) {
+            const int rl = r - before;
+            if (ncoll <= 32) {
+              uint32_t s1[1] = {(lane < ncoll) ? hist[lane] : kKeyInvalid};
+              warp_bitonic<1>(s1, lane);
+              k0 = __shfl_sync(kFull, s1[0], rl);
+              k1 = two ? __shfl_sync(kFull, s1[0], rl + 1) : k0;
+            } else {
+              uint32_t kmn = kKeyInvalid, kmx = 0u;
+              for (int i = lane; i < ncoll; i += 32) { kmn = min(kmn, hist[i]); kmx = max(kmx, hist[i]); }
+              kmn = warp_min_u(kmn); kmx = warp_max_u(kmx);
+              warp_select_hist(hist, ncoll, rl, two, lane, kmn, kmx, k0, k1);
+            }
+            done = true;
+          }
+        }
+        if (!done) {
+          SelWindow win;
+          win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = n_valid_box;
+          win.straddle = false; win.split = 0u;
+          warp_select_global(fbase, W, rc, A.dmax_bits, lane, hist, kCollCap, win, r, two, A.counters, k0, k1);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        FrameTab tb;
+        tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
+        tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
+        tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+        write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
+                         tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
+                         (float)(1.0 / A.scale_depth));
+      }
+      __syncwarp();
+    }
+    item_next = __shfl_sync(kFull, item_next, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 4. large boxes: one CTA per box
 // ------------------------------------------------------------------------------------------
 struct LargeShared {
@@ -1511,7 +2115,7 @@ static inline void prof_mark(int i, cudaStream_t st) {
 
 struct DeviceInfo {
   int sms = 0;
-  int small_ctas = 1, large_ctas = 1, tma_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
+  int small_ctas = 1, large_ctas = 1, tma_ctas = 1, hist_ctas = 1, quad_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
   bool ok = false;
   bool attrs_set = false;
 };
@@ -1548,6 +2152,16 @@ static int device_info(DeviceInfo** out) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tma_ctas, lift_tma_kernel, kTmaWarps * 32, kTmaSmemBytes);
     if (e != cudaSuccess) return (int)e;
     d.tma_ctas = std::max(d.tma_ctas, 1);
+    e = cudaFuncSetAttribute(lift_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistWarps * kHistWarpWords * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.hist_ctas, lift_hist_kernel, kHistWarps * 32, kHistWarps * kHistWarpWords * 4);
+    if (e != cudaSuccess) return (int)e;
+    d.hist_ctas = std::max(d.hist_ctas, 1);
+    e = cudaFuncSetAttribute(lift_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadWarps * kQuadWarpWords * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.quad_ctas, lift_quad_kernel, kQuadWarps * 32, kQuadWarps * kQuadWarpWords * 4);
+    if (e != cudaSuccess) return (int)e;
+    d.quad_ctas = std::max(d.quad_ctas, 1);
     d.small_ctas = std::max(d.small_ctas, 1);
     d.large_ctas = std::max(d.large_ctas, 1);
     d.attrs_set = true;
@@ -1562,12 +2176,25 @@ static int device_info(DeviceInfo** out) {
 // cuTensorMapEncodeTiled is a host-only encoder; it is resolved through the runtime so that
 // liblm3d.so has no link-time dependency on libcuda.  Returns the widest usable tile span in
 // floats (0: TMA path unusable for this tensor, the legacy warp kernel takes every small box).
+// Which kernel takes the warp boxes.  LM3D_WARP_PATH = "quad" (default: float4 loads, a lane owns four
+// consecutive pixels, histogram percentile; W % 4 != 0 tensors fall to "hist"), "hist" (scalar loads, a lane owns
+// a column, histogram percentile), "tma" (TMA tile ring, histogram percentile), "compact" (scalar loads, ballot
+// compaction + radix select: the round-1a kernel).  The last three are kept for A/B runs.  Read per call.
+enum WarpPath { kPathQuad = 0, kPathHist = 1, kPathTma = 2, kPathCompact = 3 };
+static WarpPath warp_path() {
+  const char* env = getenv("LM3D_WARP_PATH");
+  if (!env) return kPathQuad;
+  if (!strcmp(env, "hist")) return kPathHist;
+  if (!strcmp(env, "tma")) return kPathTma;
+  if (!strcmp(env, "compact")) return kPathCompact;
+  return kPathQuad;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
 static bool g_encode_tried = false;
-static bool g_tma_disabled = false;
 
 static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, TileMaps* maps) {
   if (!g_encode_tried) {
@@ -1579,9 +2206,7 @@ static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, 
       g_encode_tiled = (EncodeTiledFn)fn;
   }
   memset(maps, 0, sizeof(TileMaps));
-  const char* env = getenv("LM3D_NO_TMA");  // A/B switch for tests and benchmarks: force the direct-load warp kernel
-  g_tma_disabled = env && env[0] == '1';
-  if (!g_encode_tiled || g_tma_disabled) return 0;
+  if (!g_encode_tiled || warp_path() != kPathTma) return 0;
   if ((W & 3) != 0 || (((uintptr_t)depth) & 15) != 0) return 0;  // global strides must be multiples of 16 bytes
   int span = 0;
   for (int cls = 1; cls <= kTmaClasses; ++cls) {
@@ -1742,11 +2367,19 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1005;
 #endif
   prof_mark(3, st);
-  if (tma_span < W) {  // otherwise every warp box fits a tile class and the legacy list is provably empty
+  if (tma_span < W) {  // otherwise every warp box fits a tile class and this list is provably empty
     A.list = nullptr; A.items = ws.small_items; A.count_idx = 0; A.cursor_idx = 2;
     const int64_t want = (B + (int64_t)kSmallWarps * kSmallChunk - 1) / ((int64_t)kSmallWarps * kSmallChunk);
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->small_ctas));
-    lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
+    if (warp_path() == kPathCompact) {
+      const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->small_ctas));
+      lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
+    } else if (warp_path() == kPathQuad && (W & 3) == 0) {
+      const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->quad_ctas));
+      lift_quad_kernel<<<grid, kQuadWarps * 32, kQuadWarps * kQuadWarpWords * 4, st>>>(A);
+    } else {
+      const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->hist_ctas));
+      lift_hist_kernel<<<grid, kHistWarps * 32, kHistWarps * kHistWarpWords * 4, st>>>(A);
+    }
     g_launches += 1;
   }
 #ifdef LM3D_DEBUG_BOUNDS

@@ -379,7 +379,10 @@ def run_lm3d(args):
             traffic = None
     roofline = {
         "bound": "hbm",
-        "kernel": ["prep_frames_kernel", "prep_boxes_kernel", "lift_tma_kernel", "lift_small_kernel", "lift_large_kernel"][dom],
+        "kernel": ["prep_frames_kernel", "prep_boxes_kernel", "lift_tma_kernel",
+                   {"compact": "lift_small_kernel", "hist": "lift_hist_kernel"}.get(os.environ.get("LM3D_WARP_PATH", ""),
+                                                                                    "lift_quad_kernel"),
+                   "lift_large_kernel"][dom],
         "achieved": achieved,
         "peak": peak,
         "peak_source": peak_src,
@@ -387,8 +390,9 @@ def run_lm3d(args):
         "frac": achieved / peak,
         "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes,
-        "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_tma": kern[2], "lift_small": kern[3],
+        "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_tma": kern[2], "lift_warp": kern[3],
                       "lift_large": kern[4]},
+        "warp_path": os.environ.get("LM3D_WARP_PATH", "quad"),
         "rare_paths": {"global_fallbacks": rare[0], "narrowing_passes": rare[1], "candidate_overflows": rare[2]},
     }
 

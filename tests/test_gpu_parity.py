@@ -9,11 +9,12 @@ from parity import assert_records_match
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tma", "direct"])
+@pytest.fixture(autouse=True, params=["quad", "hist", "tma", "compact"])
 def warp_kernel_path(request, monkeypatch):
-    """Every parity case runs twice: warp boxes through the TMA-fed kernel (default) and through the
-    direct-load warp kernel (LM3D_NO_TMA=1, also what W % 4 != 0 tensors take)."""
-    monkeypatch.setenv("LM3D_NO_TMA", "1" if request.param == "direct" else "0")
+    """Every parity case runs through each warp-box kernel: "quad" (default: float4 loads + histogram
+    percentile), "hist" (scalar loads + histogram percentile; also what W % 4 != 0 tensors take), "tma" (TMA tile ring + histogram percentile; rects no tile class fits and W % 4 != 0 tensors
+    still take "hist"), "compact" (ballot compaction + radix select, kept for A/B runs)."""
+    monkeypatch.setenv("LM3D_WARP_PATH", request.param)
     return request.param
 
 
