@@ -1409,12 +1409,18 @@ __global__ void __launch_bounds__(kHistWarps * 32, LM3D_HIST_MINB) lift_hist_ker
 //     latency (ncu: 53 % of the stall samples are long-scoreboard waits on first use).
 //     Same two-pass histogram percentile as 3b / 3c.  Needs W % 4 == 0.
 // ------------------------------------------------------------------------------------------
-constexpr int kQuadWarps = 8;
+#ifndef LM3D_QUAD_WARPS
+#define LM3D_QUAD_WARPS 10
+#endif
+constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #ifndef LM3D_QUAD_MINB
-#define LM3D_QUAD_MINB 3
+#define LM3D_QUAD_MINB 2
 #endif
 #ifndef LM3D_QUAD_DEPTH
-#define LM3D_QUAD_DEPTH 4
+#define LM3D_QUAD_DEPTH 2
+#endif
+#ifndef LM3D_QUAD_BREAK
+#define LM3D_QUAD_BREAK 0
 #endif
 constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight (cp.async groups)
 constexpr int kQuadWarpWords = kHistWarpWords + kQuadDepth * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
@@ -1581,6 +1587,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
           for (int st = 0; st < nsteps; st += kQuadDepth) {
 #pragma unroll
             for (int i = 0; i < kQuadDepth; ++i) {
+#if LM3D_QUAD_BREAK
+              if (st + i >= nsteps) break;  // (uniform) the padding steps of the last group carry no pixels
+#endif
               cp_async_wait<kQuadDepth - 1>();
               const uint4 q0 = lds_u4(pipe_s + i * 512);
               cp_async_16(pipe_s + i * 512, gp, (nxt_row < rows_l) ? 16u : 0u);
@@ -1671,6 +1680,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
           for (int st = 0; st < nsteps; st += kQuadDepth) {
 #pragma unroll
             for (int i = 0; i < kQuadDepth; ++i) {
+#if LM3D_QUAD_BREAK
+              if (st + i >= nsteps) break;  // (uniform) the padding steps of the last group carry no pixels
+#endif
               cp_async_wait<kQuadDepth - 1>();
               const uint4 q0 = lds_u4(pipe_s + i * 512);
               cp_async_16(pipe_s + i * 512, gp, (nxt_row < rows_l) ? 16u : 0u);
