@@ -167,8 +167,18 @@ __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64
     int4* dst = is_tma ? reinterpret_cast<int4*>(tma_items + bt + __popc(mt & lt))
                        : reinterpret_cast<int4*>(small_items + bs + __popc(ms & lt));
     const float4* tp = reinterpret_cast<const float4*>(tab + f);
+    // quad-kernel lane geometry (see lift_quad_kernel): Q quads per row from the 16-byte aligned start, P column
+    // passes of Qp <= 16 quads, RPq = 32 / Qp rows per step -- the P (of three candidates) that covers the most
+    // rect rows per step and pass, e.g. Q = 12: P = 2, Qp = 6, RPq = 5 (30 lanes) beats P = 1 (24 lanes)
+    const int Q = (x1 - (x0 & ~3) + 4) >> 2;
+    int P = (Q + 15) >> 4, Qp = (Q + P - 1) / P, RPq = 32 / Qp;
+    for (int dp = 1; dp <= 2; ++dp) {
+      const int P2 = ((Q + 15) >> 4) + dp, Qp2 = (Q + P2 - 1) / P2, R2 = 32 / Qp2;
+      if (R2 * P > RPq * P2) { P = P2; Qp = Qp2; RPq = R2; }
+    }
+    const int nsteps = (y1 - y0 + RPq) / RPq;
     dst[0] = make_int4((int)b, f, x0, y0);
-    dst[1] = make_int4(x1, y1, 0, 0);
+    dst[1] = make_int4(x1, y1, P | (Qp << 12) | (RPq << 20), nsteps);
     reinterpret_cast<float4*>(dst)[2] = tp[0];
     reinterpret_cast<float4*>(dst)[3] = tp[1];
     reinterpret_cast<float4*>(dst)[4] = tp[2];
@@ -1413,11 +1423,11 @@ __global__ void __launch_bounds__(kHistWarps * 32, LM3D_HIST_MINB) lift_hist_ker
 //     Same two-pass histogram percentile as 3b / 3c.  Needs W % 4 == 0.
 // ------------------------------------------------------------------------------------------
 #ifndef LM3D_QUAD_WARPS
-#define LM3D_QUAD_WARPS 10
+#define LM3D_QUAD_WARPS 8
 #endif
 constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #ifndef LM3D_QUAD_MINB
-#define LM3D_QUAD_MINB 2
+#define LM3D_QUAD_MINB 3
 #endif
 #ifndef LM3D_QUAD_DEPTH
 #define LM3D_QUAD_DEPTH 2
@@ -1427,6 +1437,9 @@ constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #endif
 constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight (cp.async groups)
 constexpr int kQuadWarpWords = kHistWarpWords + kQuadDepth * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
+
+__constant__ uint32_t kRecip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,  // ceil(65536 / Qp)
+                                      7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
 
 struct AccQ {
   float mn0, mn1, mn2, mx0, mx1, mx2;
@@ -1471,6 +1484,27 @@ __device__ __forceinline__ void accum_quad_hist(const uint4 q, const uint32_t (&
 }
 
 __device__ __forceinline__ uint4 ldg_u4(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// pass 2 on one quad: two packed fmas give the four bin words; a pixel whose word is tg[j] (+ dt) is appended to the
+// lane's private column.  tg[j] - dt wraps for masked pixels (tg = 0xffffff00), which then match nothing.
+__device__ __forceinline__ void collect_quad(const uint4 q, float s4f, float kkf, const uint32_t (&tg)[4], uint32_t dt,
+                                             uint32_t& ptr) {
+  float y[4];
+  unpack2(fma2(pack2(__uint_as_float(q.x), __uint_as_float(q.y)), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+  unpack2(fma2(pack2(__uint_as_float(q.z), __uint_as_float(q.w)), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+  const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+  if (dt == 0u) {  // (uniform) the usual case: both ranks in one bin -> one compare per pixel
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, %3;\n@p st.shared.u32 [%0], %1;\n@p add.u32 %0, %0, 128;\n}"
+                   : "+r"(ptr) : "r"(bits[j]), "r"(__float_as_uint(y[j])), "r"(tg[j]) : "memory");
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("{\n.reg .pred p;\n.reg .b32 t;\nsub.u32 t, %2, %3;\nsetp.le.u32 p, t, %4;\n@p st.shared.u32 [%0], %1;\n@p add.u32 %0, %0, 128;\n}"
+                   : "+r"(ptr) : "r"(bits[j]), "r"(__float_as_uint(y[j])), "r"(tg[j]), "r"(dt) : "memory");
+  }
+}
 
 __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_kernel(const LiftArgs A) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -1527,18 +1561,11 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
       //      RPq rows per step; lane -> (row r, quad q) --------------------------------------------------
       const int xa = rc.x0 & ~3;
       const int Q = (rc.x1 - xa + 4) >> 2;
-      // P column passes of Qp <= 16 quads, RPq = 32 / Qp rows per step: take the P (of three candidates) that
-      // covers the most rect rows per step and pass, e.g. Q = 12: P = 2, Qp = 6, RPq = 5 (30 lanes) beats P = 1 (24 lanes)
-      int P = (Q + 15) >> 4, Qp = (Q + P - 1) / P, RPq = 32 / Qp;
-#pragma unroll
-      for (int dp = 1; dp <= 2; ++dp) {
-        const int P2 = ((Q + 15) >> 4) + dp, Qp2 = (Q + P2 - 1) / P2, R2 = 32 / Qp2;
-        if (R2 * P > RPq * P2) { P = P2; Qp = Qp2; RPq = R2; }
-      }
-      const int lr = (lane * ((65536 + Qp - 1) / Qp)) >> 16;  // lane / Qp (exact for lane < 32)
+      // P column passes of Qp <= 16 quads, RPq = 32 / Qp rows per step, nsteps row steps: chosen by prep_boxes_kernel
+      const int P = i1.z & 0xfff, Qp = (i1.z >> 12) & 0xff, RPq = i1.z >> 20, nsteps = i1.w;
+      const int lr = (lane * (int)kRecip16[Qp]) >> 16;  // lane / Qp (exact for lane < 32)
       const int lq = lane - lr * Qp;
       const bool active = lr < RPq;
-      const int nsteps = (rc.h + RPq - 1) / RPq;
       const uint32_t rstep = (uint32_t)(RPq * W);
       const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
       const float frp = (float)RPq;
@@ -1736,8 +1763,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
                 cp_async_commit();
                 gp += rstep;
                 nxt_row += RPq;
-                collect_px(q0.x, s4f, kkf, tg[0], dt, cptr); collect_px(q0.y, s4f, kkf, tg[1], dt, cptr);
-                collect_px(q0.z, s4f, kkf, tg[2], dt, cptr); collect_px(q0.w, s4f, kkf, tg[3], dt, cptr);
+                collect_quad(q0, s4f, kkf, tg, dt, cptr);
                 cptr = min(cptr, cend);
               }
             }
