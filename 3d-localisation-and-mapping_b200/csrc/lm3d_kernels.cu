@@ -1433,7 +1433,10 @@ constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #define LM3D_QUAD_DEPTH 2
 #endif
 #ifndef LM3D_QUAD_BREAK
-#define LM3D_QUAD_BREAK 0
+#define LM3D_QUAD_BREAK 1
+#endif
+#ifndef LM3D_QUAD_SAMPLE_E
+#define LM3D_QUAD_SAMPLE_E 2  // lattice sample = 32 * E pixels
 #endif
 constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight (cp.async groups)
 constexpr int kQuadWarpWords = kHistWarpWords + kQuadDepth * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
@@ -1540,7 +1543,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
 
       // ---- sample -> bracket -> histogram map ------------------------------------------------
       uint32_t lo = 1u, hi = kKeyMaxValid;
-      if (n_pix > 64) sample_bracket_regs<2>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
+      if (n_pix > 64) sample_bracket_regs<LM3D_QUAD_SAMPLE_E>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
       hi = min(hi, A.dmax_bits);
       // the bracket as depths [wlo_f, whi_f]; 250 of the 256 bins span it (see 3b for the map)
       float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
