@@ -2537,6 +2537,37 @@ int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, c
   return (int)e;
 }
 
+// Staging buffers of the host entry point, kept per device between calls (a sequence is usually lifted many
+// times per process; 18 cudaMalloc/cudaFree + 2 cudaMallocHost per call cost milliseconds of a 45 ms call).
+namespace {
+struct HostSlot {
+  cudaStream_t st = nullptr;
+  float* depth = nullptr;
+  double *pose = nullptr, *intr = nullptr, *boxes = nullptr, *wh = nullptr;
+  int64_t* off = nullptr;
+  int32_t* rect = nullptr;
+  lm3d_box_out* out = nullptr;
+  void* ws = nullptr;
+  int64_t* off_host = nullptr;
+};
+struct HostCache {
+  HostSlot slot[2];
+  size_t depth_bytes = 0, ws_bytes = 0;
+  int64_t frames = 0, boxes = 0;
+  bool in_use = false;
+};
+HostCache g_host_cache[64];
+std::atomic_flag g_host_lock = ATOMIC_FLAG_INIT;
+
+void host_slot_free(HostSlot& S) {
+  cudaFree(S.depth); cudaFree(S.pose); cudaFree(S.intr); cudaFree(S.wh); cudaFree(S.off);
+  cudaFree(S.boxes); cudaFree(S.rect); cudaFree(S.out); cudaFree(S.ws);
+  if (S.off_host) cudaFreeHost(S.off_host);
+  if (S.st) cudaStreamDestroy(S.st);
+  S = HostSlot();
+}
+}  // namespace
+
 int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
                          const double* intr4, const double* boxes_xyxy, const double* image_wh,
                          const int64_t* frame_off, int64_t B, double scale_depth, double max_depth_mm,
@@ -2545,6 +2576,7 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
   if (!(q_percent >= 0.0 && q_percent <= 100.0) || !(scale_depth > 0.0)) return LM3D_ERR_BAD_ARG;
   if (B == 0) return LM3D_OK;
   if (F < 1 || !depth || !pose7 || !intr4 || !boxes_xyxy || !image_wh || !frame_off || !out) return LM3D_ERR_BAD_ARG;
+  if (device < 0 || device >= 64) return LM3D_ERR_NO_DEVICE;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return LM3D_ERR_NO_DEVICE;
 
@@ -2558,37 +2590,38 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
     max_boxes = std::max(max_boxes, frame_off[f1] - frame_off[f0]);
   }
   if (frame_off[0] != 0 || frame_off[F] != B) return LM3D_ERR_BAD_ARG;
+  max_boxes = std::max<int64_t>(max_boxes, 1);
+  const size_t ws_bytes = lm3d_workspace_bytes(chunk, max_boxes);
 
-  struct Slot {
-    cudaStream_t st = nullptr;
-    float* depth = nullptr;
-    double *pose = nullptr, *intr = nullptr, *boxes = nullptr, *wh = nullptr;
-    int64_t* off = nullptr;
-    int32_t* rect = nullptr;
-    lm3d_box_out* out = nullptr;
-    void* ws = nullptr;
-    int64_t* off_host = nullptr;
-  } slot[2];
-  const size_t ws_bytes = lm3d_workspace_bytes(chunk, std::max<int64_t>(max_boxes, 1));
+  // one call at a time per process on the cached buffers; a concurrent call uses private ones
+  HostCache private_cache;
+  bool cached = !g_host_lock.test_and_set(std::memory_order_acquire);
+  HostCache& C = cached ? g_host_cache[device] : private_cache;
   int rc = LM3D_OK;
   auto ck = [&](cudaError_t err) { if (err != cudaSuccess && rc == LM3D_OK) rc = (int)err; return err == cudaSuccess; };
-  for (int s = 0; s < 2 && rc == LM3D_OK; ++s) {
-    Slot& S = slot[s];
-    ck(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
-    ck(cudaMalloc((void**)&S.depth, (size_t)chunk * frame_bytes));
-    ck(cudaMalloc((void**)&S.pose, (size_t)chunk * 7 * 8));
-    ck(cudaMalloc((void**)&S.intr, (size_t)chunk * 4 * 8));
-    ck(cudaMalloc((void**)&S.wh, (size_t)chunk * 2 * 8));
-    ck(cudaMalloc((void**)&S.off, (size_t)(chunk + 1) * 8));
-    ck(cudaMalloc((void**)&S.boxes, (size_t)std::max<int64_t>(max_boxes, 1) * 4 * 8));
-    ck(cudaMalloc((void**)&S.rect, (size_t)std::max<int64_t>(max_boxes, 1) * 16));
-    ck(cudaMalloc((void**)&S.out, (size_t)std::max<int64_t>(max_boxes, 1) * sizeof(lm3d_box_out)));
-    ck(cudaMalloc(&S.ws, ws_bytes));
-    ck(cudaMallocHost((void**)&S.off_host, (size_t)(chunk + 1) * 8));
+  const bool fits = C.slot[0].st && C.depth_bytes >= (size_t)chunk * frame_bytes && C.frames >= chunk && C.boxes >= max_boxes &&
+                    C.ws_bytes >= ws_bytes;
+  if (!fits) {
+    for (int s = 0; s < 2; ++s) host_slot_free(C.slot[s]);
+    for (int s = 0; s < 2 && rc == LM3D_OK; ++s) {
+      HostSlot& S = C.slot[s];
+      ck(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+      ck(cudaMalloc((void**)&S.depth, (size_t)chunk * frame_bytes));
+      ck(cudaMalloc((void**)&S.pose, (size_t)chunk * 7 * 8));
+      ck(cudaMalloc((void**)&S.intr, (size_t)chunk * 4 * 8));
+      ck(cudaMalloc((void**)&S.wh, (size_t)chunk * 2 * 8));
+      ck(cudaMalloc((void**)&S.off, (size_t)(chunk + 1) * 8));
+      ck(cudaMalloc((void**)&S.boxes, (size_t)max_boxes * 4 * 8));
+      ck(cudaMalloc((void**)&S.rect, (size_t)max_boxes * 16));
+      ck(cudaMalloc((void**)&S.out, (size_t)max_boxes * sizeof(lm3d_box_out)));
+      ck(cudaMalloc(&S.ws, ws_bytes));
+      ck(cudaMallocHost((void**)&S.off_host, (size_t)(chunk + 1) * 8));
+    }
+    C.depth_bytes = (size_t)chunk * frame_bytes; C.frames = chunk; C.boxes = max_boxes; C.ws_bytes = ws_bytes;
   }
   int k = 0;
   for (int64_t f0 = 0; f0 < F && rc == LM3D_OK; f0 += chunk, k ^= 1) {
-    Slot& S = slot[k];
+    HostSlot& S = C.slot[k];
     const int64_t f1 = std::min(F, f0 + chunk), nf = f1 - f0;
     const int64_t b0 = frame_off[f0], nb = frame_off[f1] - b0;
     ck(cudaStreamSynchronize(S.st));  // slot free again (its previous D2H finished)
@@ -2603,17 +2636,20 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
       if (rc == LM3D_OK) rc = lm3d_scale_boxes(S.boxes, S.wh, S.off, nf, nb, W, H, S.rect, S.st);
       if (rc == LM3D_OK)
         rc = lm3d_lift_boxes(S.depth, nf, H, W, S.pose, S.intr, S.rect, S.off, nb, scale_depth, max_depth_mm,
-                             q_percent, S.out, nullptr, S.ws, ws_bytes, S.st);
+                             q_percent, S.out, nullptr, S.ws, C.ws_bytes, S.st);
       ck(cudaMemcpyAsync(out + b0, S.out, (size_t)nb * sizeof(lm3d_box_out), cudaMemcpyDeviceToHost, S.st));
     }
   }
-  for (int s = 0; s < 2; ++s) {
-    Slot& S = slot[s];
-    if (S.st) ck(cudaStreamSynchronize(S.st));
-    cudaFree(S.depth); cudaFree(S.pose); cudaFree(S.intr); cudaFree(S.wh); cudaFree(S.off);
-    cudaFree(S.boxes); cudaFree(S.rect); cudaFree(S.out); cudaFree(S.ws);
-    if (S.off_host) cudaFreeHost(S.off_host);
-    if (S.st) cudaStreamDestroy(S.st);
+  for (int s = 0; s < 2; ++s)
+    if (C.slot[s].st) ck(cudaStreamSynchronize(C.slot[s].st));
+  if (cached) {
+    if (rc != LM3D_OK) {  // do not keep buffers of a failed call
+      for (int s = 0; s < 2; ++s) host_slot_free(C.slot[s]);
+      C = HostCache();
+    }
+    g_host_lock.clear(std::memory_order_release);
+  } else {
+    for (int s = 0; s < 2; ++s) host_slot_free(private_cache.slot[s]);
   }
   return rc;
 }
