@@ -52,6 +52,17 @@ def test_config_shapes(cuda_device, name, frames):
     assert_records_match(rec, os_, run_oracle(seq, rect4))
 
 
+def test_large_boxes_legacy_cta_kernel(cuda_device, monkeypatch):
+    """CTA boxes default to lift_block_kernel (float4 quads + histogram percentile); LM3D_LARGE_PATH=legacy keeps
+    the round-1a CTA kernel (also what W % 4 != 0 tensors take) -- both must agree with the oracle."""
+    from lm3d import synth
+
+    monkeypatch.setenv("LM3D_LARGE_PATH", "legacy")
+    seq = synth.make_config("C3", frames=2)
+    rec, os_, rect4 = run_cuda(seq, cuda_device)
+    assert_records_match(rec, os_, run_oracle(seq, rect4))
+
+
 @pytest.mark.parametrize("q", [0.0, 10.0, 37.5, 50.0, 90.0, 100.0])
 def test_percentiles(cuda_device, q):
     from lm3d import synth
