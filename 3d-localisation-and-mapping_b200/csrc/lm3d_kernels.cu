@@ -1435,6 +1435,9 @@ constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #ifndef LM3D_QUAD_BREAK
 #define LM3D_QUAD_BREAK 1
 #endif
+#ifndef LM3D_QUAD_P2_LDG
+#define LM3D_QUAD_P2_LDG 0  // pass 2 through plain LDG.128 with a one-step register prefetch instead of cp.async
+#endif
 #ifndef LM3D_QUAD_SAMPLE_E
 #define LM3D_QUAD_SAMPLE_E 2  // lattice sample = 32 * E pixels
 #endif
@@ -1747,6 +1750,22 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
             uint32_t off = (uint32_t)((rc.y0 + row_l) * W + col0);
             const float* gp = fbase + off;
             const int rows_l = rc.h - row_l;
+#if LM3D_QUAD_P2_LDG
+            // pass 2 hits L2: plain LDG.128, the next step's quad requested before this one is scanned
+            uint4 qn = make_uint4(0u, 0u, 0u, 0u);
+            if (0 < rows_l) qn = ldg_u4(gp);
+            int nxt_row = RPq;
+#pragma unroll 1
+            for (int st = 0; st < nsteps; ++st) {
+              const uint4 q0 = qn;
+              gp += rstep;
+              qn = make_uint4(0u, 0u, 0u, 0u);
+              if (nxt_row < rows_l) qn = ldg_u4(gp);
+              nxt_row += RPq;
+              collect_quad<128>(q0, s4f, kkf, tg, dt, cptr);
+              cptr = min(cptr, cend);
+            }
+#else
 #pragma unroll
             for (int i = 0; i < kQuadDepth; ++i) {
               cp_async_16(pipe_s + i * 512, gp, (i * RPq < rows_l) ? 16u : 0u);
@@ -1772,6 +1791,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
               }
             }
             cp_async_wait<0>();
+#endif
           }
           __syncwarp();
           if (!__any_sync(kFull, cptr >= cend)) {
