@@ -33,7 +33,10 @@ namespace lm3d {
 constexpr int kSmallMaxPix = 8160;       // warp-per-box up to this rect area (255 px per lane: 8-bit packed counters)
 constexpr int kSmallWarps = 8;           // warps per CTA in the small kernel
 constexpr int kSmallCap = 2048;          // candidate keys per warp (8 KB), dense
-constexpr int kSmallChunk = 2;           // boxes claimed per atomic
+#ifndef LM3D_SMALL_CHUNK
+#define LM3D_SMALL_CHUNK 2
+#endif
+constexpr int kSmallChunk = LM3D_SMALL_CHUNK;  // boxes claimed per atomic
 #ifndef LM3D_BRACKET_Z
 #define LM3D_BRACKET_Z 3.0f
 #endif
