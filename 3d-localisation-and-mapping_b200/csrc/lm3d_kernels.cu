@@ -2599,6 +2599,23 @@ __global__ void __launch_bounds__(256) frame_cloud_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// depth ingest (SURVEY 8f "next" #2: /root/reference/src/detector/dataset.py:70-77): a decoded depth PNG is 8UC4,
+// the four bytes of each pixel being one fp32 METRE value; the reference reinterprets and multiplies by 1000 in
+// fp32.  Pure streaming (4 B in, 4 B out per pixel): float4 loads / stores, grid-stride, in place allowed.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ingest_depth_kernel(const float* __restrict__ raw, int64_t n, float scale,
+                                                           float* __restrict__ out) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(raw)[i];
+    v.x = __fmul_rn(v.x, scale); v.y = __fmul_rn(v.y, scale); v.z = __fmul_rn(v.z, scale); v.w = __fmul_rn(v.w, scale);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(n4 << 2) + threadIdx.x] = __fmul_rn(raw[(n4 << 2) + threadIdx.x], scale);
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static std::atomic<int64_t> g_launches{0};
@@ -2908,6 +2925,21 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   prof_mark(5, st);
   g_prof_valid = g_profile;
   g_launches += 3;
+  return (int)cudaGetLastError();
+}
+
+int lm3d_ingest_depth(const void* raw_8uc4, int64_t n_pixels, float scale, float* depth_out, void* stream) {
+  if (n_pixels < 0) return LM3D_ERR_BAD_ARG;
+  if (n_pixels == 0) return LM3D_OK;
+  if (!raw_8uc4 || !depth_out) return LM3D_ERR_BAD_ARG;
+  if ((((uintptr_t)raw_8uc4 | (uintptr_t)depth_out) & 15) != 0) return LM3D_ERR_ALIGNMENT;
+  DeviceInfo* dev = nullptr;
+  int rc = device_info(&dev);
+  if (rc != LM3D_OK) return rc;
+  const int64_t want = ((n_pixels >> 2) + 255) / 256;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * 8));
+  ingest_depth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(raw_8uc4), n_pixels, scale, depth_out);
+  g_launches += 1;
   return (int)cudaGetLastError();
 }
 

@@ -96,6 +96,14 @@ int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, c
                           const double* intr4, double scale_depth, double max_depth_mm, float* xyz,
                           int32_t* n_valid, void* stream);
 
+/* Depth ingest: replaces the byte reinterpretation + metres -> millimetres scaling of
+ * ImageDataset._load_depth_image (src/detector/dataset.py:70-77) for a whole batch of decoded depth PNGs.
+ *   raw_8uc4  [n_pixels,4] u8: the PNG pixels as cv2.imread(IMREAD_UNCHANGED) returns them, i.e. the bytes of
+ *             one fp32 metre value per pixel (device pointer, 16-byte aligned)
+ *   depth_out [n_pixels] f32 = fp32(raw) * scale, computed in fp32 like the reference (scale = 1000);
+ *             may alias raw_8uc4 (in place)                                                          */
+int lm3d_ingest_depth(const void* raw_8uc4, int64_t n_pixels, float scale, float* depth_out, void* stream);
+
 /* Host-buffer convenience for bindings without a device allocator (the e2e path): copies the
  * sequence to the device in frame chunks on two streams (copy overlapped with compute), runs
  * lm3d_scale_boxes + lm3d_lift_boxes, copies the records back, synchronises.  All pointers are

@@ -373,3 +373,25 @@ def union_pixels_per_frame(rect4, frame_off, H, W):
         cover = diff.cumsum(0).cumsum(1)[:H, :W]
         U[f] = int((cover > 0).sum())
     return U
+
+
+# ---------------------------------------------------------------------------------------
+# Depth / calibration ingest (SURVEY.md 8f "next" #2).  Unlike the lift helpers this part of the
+# reference IS in the tree, and tests/golden/depth_ingest.npz is produced by running it unmodified.
+# ---------------------------------------------------------------------------------------
+def decode_depth_8uc4(raw_u8: np.ndarray, scale: float = 1000.0) -> np.ndarray:
+    """``[...,H,W,4]`` uint8 (a depth PNG as ``cv2.imread(..., IMREAD_UNCHANGED)`` returns it: the four bytes of
+    each fp32 METRE value) -> ``[...,H,W]`` float32 MILLIMETRES.  Follows
+    ``/root/reference/src/detector/dataset.py:70-77``: reinterpret the bytes as float32, multiply IN float32."""
+    raw_u8 = np.ascontiguousarray(raw_u8, dtype=np.uint8)
+    if raw_u8.shape[-1] != 4:
+        raise ValueError("expected [...,H,W,4] uint8")
+    metres = raw_u8.view(np.float32).reshape(raw_u8.shape[:-1])
+    return metres * np.float32(scale)
+
+
+def intrinsics_row(calibration: dict, depth_width: int) -> np.ndarray:
+    """Calibration dict of ``dataset.py:102-121`` -> ``[fx,fy,cx,cy]`` at depth resolution (R1,
+    ``pose_processor.py:133-137``: all four divided by the WIDTH ratio)."""
+    fx, fy, cx, cy = rescale_intrinsics(calibration, depth_width)
+    return np.array([fx, fy, cx, cy], dtype=np.float64)
