@@ -63,9 +63,16 @@ __device__ __forceinline__ float warp_max_f(float v) { return ord2f(warp_max_u(f
 // The shuffle stages run as a rolled loop over (size, stride): the instruction cache, not
 // the ALUs, is what a fully unrolled network (2k+ instructions) costs this kernel.
 // ---------------------------------------------------------------------------------------
+#ifndef LM3D_SORT_UNROLL
+#define LM3D_SORT_UNROLL 0  // 1: fully unrolled shuffle network (more SASS, fewer loop instructions)
+#endif
 template <int E>
 __device__ __forceinline__ void bitonic_shuffle_stages(uint32_t (&k)[E], int lane, int size, int stride) {
+#if LM3D_SORT_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (; stride > 0; stride >>= 1) {
     const bool lower = ((lane & stride) == 0);
 #pragma unroll
@@ -79,7 +86,11 @@ __device__ __forceinline__ void bitonic_shuffle_stages(uint32_t (&k)[E], int lan
 
 template <int E>
 __device__ __forceinline__ void warp_bitonic(uint32_t (&k)[E], int lane) {
+#if LM3D_SORT_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int size = 2; size <= 32; size <<= 1) bitonic_shuffle_stages<E>(k, lane, size, size >> 1);
 #pragma unroll
   for (int size = 64; size <= 32 * E; size <<= 1) {
