@@ -2201,7 +2201,10 @@ struct BlockShared {
   int b_lo, b_hi, before, end, ncoll, overflow;
 };
 
-__global__ void __launch_bounds__(kBlkThreads, 3) lift_block_kernel(const LiftArgs A) {
+#ifndef LM3D_BLK_MINB
+#define LM3D_BLK_MINB 3
+#endif
+__global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(const LiftArgs A) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* hist = smem_u32;
   const uint32_t* coll = smem_u32 + kBlkHistWords;
