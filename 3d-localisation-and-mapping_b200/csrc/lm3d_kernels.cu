@@ -1893,12 +1893,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
           done = true;
         }
       }
-#ifdef LM3D_DIAG_NO_WRITE
-      if (lane == 0) A.out[b].z_q = __uint_as_float(k0 + k1) + S0 + SU + SV + mn[0] + mn[1] + mn[2] + mx[0] + mx[1] + mx[2] + (float)n_valid_box;
-      if (false) {
-#else
       if (lane == 0) {
-#endif
         const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
         FrameTab tb;
         tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
