@@ -1204,13 +1204,14 @@ __global__ void __launch_bounds__(kHistWarps * 32, LM3D_HIST_MINB) lift_hist_ker
       uint32_t lo = 1u, hi = kKeyMaxValid;
       if (n_pix > 64) sample_bracket_regs<2>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
       hi = min(hi, A.dmax_bits);
+      float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
       float s4f, kkf;
-      {
-        const float lo_f = __uint_as_float(lo), hi_f = __uint_as_float(max(hi, 1u));
-        const float wd = hi_f - lo_f;
-        s4f = (wd > 0.f) ? fminf(1000.f / wd, 2097152.f / hi_f) : 0.f;
-        kkf = fmaf(-lo_f, s4f, 33554432.f + 4.f * 35.f);
-      }
+      auto set_map = [&]() {
+        const float wd = whi_f - wlo_f;
+        s4f = (wd > 0.f) ? fminf(1000.f / wd, 2097152.f / whi_f) : 0.f;
+        kkf = fmaf(-wlo_f, s4f, 33554432.f + 4.f * 35.f);
+      };
+      set_map();
       const float ylo = 33554432.f + 4.f * (float)lane, yhi = 33554432.f + 4.f * (float)(288 + lane);
       const uint32_t hist_bias = hist_s - 0x30000000u;
 #pragma unroll
@@ -1288,118 +1289,161 @@ __global__ void __launch_bounds__(kHistWarps * 32, LM3D_HIST_MINB) lift_hist_ker
       mn[0] = warp_min_f(acc.mn0); mn[1] = warp_min_f(acc.mn1); mn[2] = warp_min_f(acc.mn2);
       mx[0] = warp_max_f(acc.mx0); mx[1] = warp_max_f(acc.mx1); mx[2] = warp_max_f(acc.mx2);
 
-      // ---- which bins hold the target ranks? ----------------------------------------------------
+      // ---- exact order statistics: scan -> collect -> select, with the same bounded refinement as lift_quad ----
       int r = 0; bool two = false; double gamma = 0.0;
       if (n_valid_box > 0) order_ranks(n_valid_box, A.quant, r, two, gamma);
       const int r1 = r + (two ? 1 : 0);
-      __syncwarp();
-      int b_lo = -1, b_hi = -1, before = 0, n_coll = 0;
-      {
-        const int below_all = warp_sum_i((int)hist[lane]), above = warp_sum_i((int)hist[288 + lane]);
-        const uint4 h0 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane], h1 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane + 1];
-        const int c[8] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
-        int tot = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tot += c[i];
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(kFull, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int in_all = __shfl_sync(kFull, incl, 31);
-        const int below = below_all - (below_all + in_all + above - n_valid_box);
-        int cum = below + incl - tot;
-        int my_lo = -1, my_hi = -1, my_before = 0, my_end = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (r >= cum && r < cum + c[i]) { my_lo = 32 + lane * 8 + i; my_before = cum; }
-          if (r1 >= cum && r1 < cum + c[i]) { my_hi = 32 + lane * 8 + i; my_end = cum + c[i]; }
-          cum += c[i];
-        }
-        const uint32_t m_lo = __ballot_sync(kFull, my_lo >= 0), m_hi = __ballot_sync(kFull, my_hi >= 0);
-        if (n_valid_box > 0 && m_lo && m_hi) {
-          b_lo = __shfl_sync(kFull, my_lo, __ffs(m_lo) - 1);
-          before = __shfl_sync(kFull, my_before, __ffs(m_lo) - 1);
-          b_hi = __shfl_sync(kFull, my_hi, __ffs(m_hi) - 1);
-          n_coll = __shfl_sync(kFull, my_end, __ffs(m_hi) - 1) - before;
-        }
-      }
-      const bool collect = (b_lo >= 32) && (n_coll <= kCollCap);
-      const uint32_t tgt = 0x4C000000u + (uint32_t)max(b_lo, 0), dt = collect ? (uint32_t)(b_hi - b_lo) : 0u;
-
-      // ---- pass 2: re-read the rect (L1 / L2), keep the keys of the target bins in private columns ----
-      uint32_t cptr = coll_s;
-      const uint32_t cend = coll_s + kCollRows * 128;
-      if (collect) {
-        for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
-          const bool col_ok = cx0 + lm.lc < rc.w;
-          const uint32_t tgt_lane = col_ok ? tgt : 0xffffff00u;  // idle lanes match nothing
-          uint32_t off = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx0 + lm.lc : 0)) + (uint32_t)(lm.lr * W);
-          int k = 0;
-#pragma unroll 1
-          for (; k + 4 <= k_full; k += 4) {
-            const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
-            const uint32_t q0 = __float_as_uint(__ldg(fbase + off)), q1 = __float_as_uint(__ldg(fbase + o1)),
-                           q2 = __float_as_uint(__ldg(fbase + o2)), q3 = __float_as_uint(__ldg(fbase + o3));
-            collect_px(q0, s4f, kkf, tgt_lane, dt, cptr);
-            collect_px(q1, s4f, kkf, tgt_lane, dt, cptr);
-            collect_px(q2, s4f, kkf, tgt_lane, dt, cptr);
-            collect_px(q3, s4f, kkf, tgt_lane, dt, cptr);
-            cptr = min(cptr, cend);
-            off += 4 * rpw;
-          }
-#pragma unroll 1
-          for (; k < k_all; ++k) {
-            const int ry = k * RP + lm.lr;
-            if (ry < rc.h) collect_px(__float_as_uint(__ldg(fbase + off)), s4f, kkf, tgt_lane, dt, cptr);
-            cptr = min(cptr, cend);
-            off += rpw;
-          }
-        }
-      }
-
-      // ---- exact order statistics ----------------------------------------------------------------
       uint32_t k0 = 0, k1 = 0;
-      if (n_valid_box > 0) {
+      bool done = (n_valid_box == 0);
+#pragma unroll 1
+      for (int attempt = 0; !done; ++attempt) {
+        if (attempt > 0) {  // histogram-only pass over the corrected window
+          if (lane == 0) atomicAdd(&A.counters[5], 1);
+#pragma unroll
+          for (int i = 0; i < kHistWords / 32; ++i) hist[i * 32 + lane] = 0u;
+          __syncwarp();
+          for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
+            const bool col_ok = cx0 + lm.lc < rc.w;
+            const uint32_t dmax_lane = col_ok ? A.dmax_bits : 0u;
+            uint32_t off = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx0 + lm.lc : 0)) + (uint32_t)(lm.lr * W);
+#pragma unroll 1
+            for (int k = 0; k < k_all; ++k) {
+              const int ry = k * RP + lm.lr;
+              const uint32_t bits = (ry < rc.h) ? __float_as_uint(__ldg(fbase + off)) : 0u;
+              const uint32_t key = key_valid(bits, dmax_lane) ? bits : 0x7fffffffu;
+              const float yc = fminf(fmaxf(fmaf(__uint_as_float(key), s4f, kkf), ylo), yhi);
+              asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias) : "memory");
+              off += rpw;
+            }
+          }
+        }
         __syncwarp();
-        bool done = false;
-        if (collect && !__any_sync(kFull, cptr >= cend)) {
-          const int cnt_l = (int)((cptr - coll_s) >> 7);
-          const int rows = (int)warp_max_u((uint32_t)cnt_l);
-          int ncoll = 0;
-          for (int row = 0; row < rows; ++row) {
-            const uint32_t key = (row < cnt_l) ? coll[row * 32 + lane] : 0u;
-            const bool in = key_valid(key, A.dmax_bits);
-            const uint32_t bal = __ballot_sync(kFull, in);
-            const int pos = ncoll + __popc(bal & lt_mask);
-            if (in && pos < kCollCap) hist[pos] = key;
-            ncoll += __popc(bal);
+        int b_lo = -1, b_hi = -1, before = 0, n_coll = 0;
+        bool miss_low = false;
+        {
+          const int below_all = warp_sum_i((int)hist[lane]), above = warp_sum_i((int)hist[288 + lane]);
+          const uint4 h0 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane], h1 = reinterpret_cast<const uint4*>(hist + 32)[2 * lane + 1];
+          const int c[8] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+          int tot = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tot += c[i];
+          int incl = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const int in_all = __shfl_sync(kFull, incl, 31);
+          const int below = below_all - (below_all + in_all + above - n_valid_box);
+          miss_low = r < below;
+          int cum = below + incl - tot;
+          int my_lo = -1, my_hi = -1, my_before = 0, my_end = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (r >= cum && r < cum + c[i]) { my_lo = 32 + lane * 8 + i; my_before = cum; }
+            if (r1 >= cum && r1 < cum + c[i]) { my_hi = 32 + lane * 8 + i; my_end = cum + c[i]; }
+            cum += c[i];
+          }
+          const uint32_t m_lo = __ballot_sync(kFull, my_lo >= 0), m_hi = __ballot_sync(kFull, my_hi >= 0);
+          if (m_lo && m_hi) {
+            b_lo = __shfl_sync(kFull, my_lo, __ffs(m_lo) - 1);
+            before = __shfl_sync(kFull, my_before, __ffs(m_lo) - 1);
+            b_hi = __shfl_sync(kFull, my_hi, __ffs(m_hi) - 1);
+            n_coll = __shfl_sync(kFull, my_end, __ffs(m_hi) - 1) - before;
+          }
+        }
+        const bool found = b_lo >= 32;
+        bool overfull = found && n_coll > kCollCap;
+        if (found && !overfull) {
+          // ---- pass 2: re-read the rect (L1 / L2), keep the keys of the target bins in private columns ----
+          const uint32_t tgt = 0x4C000000u + (uint32_t)b_lo, dt = (uint32_t)(b_hi - b_lo);
+          uint32_t cptr = coll_s;
+          const uint32_t cend = coll_s + kCollRows * 128;
+          for (int cx0 = 0; cx0 < rc.w; cx0 += lm.G) {
+            const bool col_ok = cx0 + lm.lc < rc.w;
+            const uint32_t tgt_lane = col_ok ? tgt : 0xffffff00u;  // idle lanes match nothing
+            uint32_t off = (uint32_t)(rc.y0 * W + rc.x0 + (col_ok ? cx0 + lm.lc : 0)) + (uint32_t)(lm.lr * W);
+            int k = 0;
+#pragma unroll 1
+            for (; k + 4 <= k_full; k += 4) {
+              const uint32_t o1 = off + rpw, o2 = o1 + rpw, o3 = o2 + rpw;
+              const uint32_t q0 = __float_as_uint(__ldg(fbase + off)), q1 = __float_as_uint(__ldg(fbase + o1)),
+                             q2 = __float_as_uint(__ldg(fbase + o2)), q3 = __float_as_uint(__ldg(fbase + o3));
+              collect_px(q0, s4f, kkf, tgt_lane, dt, cptr);
+              collect_px(q1, s4f, kkf, tgt_lane, dt, cptr);
+              collect_px(q2, s4f, kkf, tgt_lane, dt, cptr);
+              collect_px(q3, s4f, kkf, tgt_lane, dt, cptr);
+              cptr = min(cptr, cend);
+              off += 4 * rpw;
+            }
+#pragma unroll 1
+            for (; k < k_all; ++k) {
+              const int ry = k * RP + lm.lr;
+              if (ry < rc.h) collect_px(__float_as_uint(__ldg(fbase + off)), s4f, kkf, tgt_lane, dt, cptr);
+              cptr = min(cptr, cend);
+              off += rpw;
+            }
           }
           __syncwarp();
-          if (ncoll == n_coll) {
-            const int rl = r - before;
-            if (ncoll <= 32) {
-              uint32_t s1[1] = {(lane < ncoll) ? hist[lane] : kKeyInvalid};
-              warp_bitonic<1>(s1, lane);
-              k0 = __shfl_sync(kFull, s1[0], rl);
-              k1 = two ? __shfl_sync(kFull, s1[0], rl + 1) : k0;
-            } else {
-              uint32_t kmn = kKeyInvalid, kmx = 0u;
-              for (int i = lane; i < ncoll; i += 32) { kmn = min(kmn, hist[i]); kmx = max(kmx, hist[i]); }
-              kmn = warp_min_u(kmn); kmx = warp_max_u(kmx);
-              warp_select_hist(hist, ncoll, rl, two, lane, kmn, kmx, k0, k1);
+          if (!__any_sync(kFull, cptr >= cend)) {
+            const int cnt_l = (int)((cptr - coll_s) >> 7);
+            const int rows = (int)warp_max_u((uint32_t)cnt_l);
+            int ncoll = 0;
+            for (int row = 0; row < rows; ++row) {
+              const uint32_t key = (row < cnt_l) ? coll[row * 32 + lane] : 0u;
+              const bool in = key_valid(key, A.dmax_bits);
+              const uint32_t bal = __ballot_sync(kFull, in);
+              const int pos = ncoll + __popc(bal & lt_mask);
+              if (in && pos < kCollCap) hist[pos] = key;
+              ncoll += __popc(bal);
             }
-            done = true;
+            __syncwarp();
+            if (ncoll == n_coll) {
+              const int rl = r - before;
+              if (ncoll <= 32) {
+                uint32_t s1[1] = {(lane < ncoll) ? hist[lane] : kKeyInvalid};
+                warp_bitonic<1>(s1, lane);
+                k0 = __shfl_sync(kFull, s1[0], rl);
+                k1 = two ? __shfl_sync(kFull, s1[0], rl + 1) : k0;
+              } else {
+                uint32_t kmn = kKeyInvalid, kmx = 0u;
+                for (int i = lane; i < ncoll; i += 32) { kmn = min(kmn, hist[i]); kmx = max(kmx, hist[i]); }
+                kmn = warp_min_u(kmn); kmx = warp_max_u(kmx);
+                warp_select_hist(hist, ncoll, rl, two, lane, kmn, kmx, k0, k1);
+              }
+              done = true;
+            }
+          } else {
+            overfull = true;
+          }
+          __syncwarp();
+        }
+        if (done) break;
+        bool refine = attempt < 2 && s4f > 0.f;
+        if (refine) {
+          if (overfull) {
+            const float nlo = wlo_f + (4.f * (float)(b_lo - 35) - 4.f) / s4f, nhi = wlo_f + (4.f * (float)(b_hi - 35) + 4.f) / s4f;
+            refine = (nhi - nlo) < 0.5f * (whi_f - wlo_f);
+            wlo_f = fmaxf(nlo, 1e-30f); whi_f = fmaxf(nhi, wlo_f);
+          } else if (miss_low) {
+            const float ov = 0.02f * (whi_f - wlo_f);
+            whi_f = wlo_f + ov; wlo_f = 0.5f * wlo_f;
+          } else {
+            const float ov = 0.02f * (whi_f - wlo_f);
+            wlo_f = fmaxf(whi_f - ov, 1e-30f); whi_f = fminf(2.f * whi_f, __uint_as_float(min(A.dmax_bits, kKeyMaxValid)));
+            refine = whi_f > wlo_f;
           }
         }
-        if (!done) {
+        if (refine) {
+          set_map();
+        } else {
           SelWindow win;
           win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = n_valid_box;
           win.straddle = false; win.split = 0u;
           warp_select_global(fbase, W, rc, A.dmax_bits, lane, hist, kCollCap, win, r, two, A.counters, k0, k1);
+          __syncwarp();
+          done = true;
         }
-        __syncwarp();
       }
       if (lane == 0) {
         const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
