@@ -1494,8 +1494,13 @@ constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #ifndef LM3D_QUAD_SAMPLE_E
 #define LM3D_QUAD_SAMPLE_E 2  // lattice sample = 32 * E pixels
 #endif
-constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight (cp.async groups)
-constexpr int kQuadWarpWords = kHistWarpWords + kQuadDepth * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
+constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight in pass 1 (cp.async groups)
+#ifndef LM3D_QUAD_DEPTH2
+#define LM3D_QUAD_DEPTH2 2   // ... and in pass 2 (4, 6, 8 measured slower)
+#endif
+constexpr int kQuadDepth2 = LM3D_QUAD_DEPTH2;
+constexpr int kQuadSlotsMax = kQuadDepth > kQuadDepth2 ? kQuadDepth : kQuadDepth2;
+constexpr int kQuadWarpWords = kHistWarpWords + kQuadSlotsMax * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
 
 __constant__ uint32_t kRecip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,  // ceil(65536 / Qp)
                                       7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
@@ -1848,16 +1853,16 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
             }
 #else
 #pragma unroll
-            for (int i = 0; i < kQuadDepth; ++i) {
+            for (int i = 0; i < kQuadDepth2; ++i) {
               cp_async_16(pipe_s + i * 512, gp, (i * RPq < rows_l) ? 16u : 0u);
               cp_async_commit();
               gp += rstep;
             }
-            int nxt_row = kQuadDepth * RPq;
+            int nxt_row = kQuadDepth2 * RPq;
 #pragma unroll 1
-            for (int st = 0; st < nsteps; st += kQuadDepth) {
+            for (int st = 0; st < nsteps; st += kQuadDepth2) {
 #pragma unroll
-              for (int i = 0; i < kQuadDepth; ++i) {
+              for (int i = 0; i < kQuadDepth2; ++i) {
 #if LM3D_QUAD_BREAK
                 if (st + i >= nsteps) break;
 #endif
