@@ -358,6 +358,31 @@ __device__ __forceinline__ void write_record(float* __restrict__ outw, float* __
 
 // fp32 finalisation for warp boxes (<= 8160 pixels: fp32 sums of centred terms are exact to
 // ~1e-6 relative; the CTA kernel keeps the fp64 version above).
+// The words of a record that depend on the percentile depth (corners, depth, order statistics), recomputed by
+// lift_resolve_kernel for the boxes whose order statistics the main kernel deferred; same expressions, in the same
+// order, as write_record_f32 below, so a deferred box is bit-identical to a directly resolved one.
+__device__ __forceinline__ void write_record_depth_f32(float* __restrict__ outw, float* __restrict__ ostats,
+                                                       const FrameTab& tb, int x0, int y0, int x1, int y1, uint32_t k0,
+                                                       uint32_t k1, float gamma, float inv_scale) {
+  const float dlo = __uint_as_float(k0), dhi = __uint_as_float(k1);
+  const float diff = dhi - dlo;  // numpy _lerp, both branches
+  const float dq = (gamma >= 0.5f) ? dhi - diff * (1.0f - gamma) : dlo + diff * gamma;
+  const float fu[2] = {(float)x0, (float)x1}, fv[2] = {(float)y0, (float)y1};
+  const int cui[4] = {0, 0, 1, 1}, cvi[4] = {0, 1, 1, 0};
+  float w[12];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      w[c * 3 + k] = fmaf(dq, fmaf(tb.a[k], fu[cui[c]], fmaf(tb.b[k], fv[cvi[c]], tb.c[k])), tb.t[k]);
+  }
+  float4* o4 = reinterpret_cast<float4*>(outw);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  outw[21] = dq * inv_scale;
+  if (ostats) { ostats[0] = dlo; ostats[1] = dhi; }
+}
+
 __device__ __forceinline__ void write_record_f32(float* __restrict__ outw, float* __restrict__ ostats,
                                                  const FrameTab& tb, int x0, int y0, int x1, int y1, float uc,
                                                  float vc, float s0, float su, float sv, const float (&mn)[3],

@@ -53,8 +53,9 @@ struct Workspace {
   void* small_items;    // [B] WorkItem (80 B): everything a warp needs for one box, one load level
   void* tma_items;      // [B] WorkItem: warp boxes that take the TMA-fed kernel
   int32_t* large_list;  // [B]
+  int32_t* deferred;    // [B] int4 {item, key window lo, hi, -}: boxes lift_quad_kernel leaves to lift_resolve_kernel
   int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor, 4..6 rare-path stats,
-                        //       8 n_tma, 9 tma cursor
+                        //       8 n_tma, 9 tma cursor, 10 n_deferred, 11 deferred cursor
 };
 
 struct __align__(16) WorkItem {
@@ -78,7 +79,9 @@ static size_t workspace_layout(int64_t F, int64_t B, char* base, Workspace* ws) 
   char* sl = take((size_t)B * 80);
   char* tl = take((size_t)B * 80);
   char* ll = take((size_t)B * 4);
+  char* dl = take((size_t)B * 16);
   if (ws) {
+    ws->deferred = (int32_t*)dl;
     ws->counters = (int32_t*)c;
     ws->tab = (FrameTab*)t;
     ws->box_frame = (int32_t*)bf;
@@ -235,6 +238,7 @@ struct LiftArgs {
   const FrameTab* tab;
   const int32_t* list;
   const void* items;
+  int32_t* deferred;
   int32_t* counters;
   int count_idx, cursor_idx;
   int H, W;
@@ -1571,6 +1575,136 @@ __device__ __forceinline__ void collect_quad(const uint4 q, float s4f, float kkf
   }
 }
 
+// Exact select for the boxes the fp32 histogram map of lift_quad_kernel does not resolve (heavy ties, coarsely
+// quantised depth, a bracket that missed twice); runs in lift_resolve_kernel, so that it costs the pixel loops of
+// the main kernel neither registers nor instruction-cache footprint (measured: calling it from lift_quad_kernel,
+// even out of line, moved the register allocation of the pixel loops and cost 8-12 % on C2).  Radix-256 select in
+// KEY space over the window [wlo, whi] (a hint from the caller, verified here; the full key range otherwise): each
+// round is ONE walk of the rect that counts the keys under the window and, per bin, the keys and their exact
+// min / max (shared atomics).  The round ends with the answer -- ranks straddling two bins (max of one, min of
+// the other), a single-valued bin (ties), <= kCollCap keys left to sort -- or with the window tightened to the
+// exact key range of one bin, which strictly shrinks it: terminates whatever the data, 2-3 walks in practice.
+__device__ __noinline__ void quad_select_exact(const float* __restrict__ depth, const int4* __restrict__ ip, int H, int W,
+                                              uint32_t dmax_bits, uint32_t* hist, int r, bool two, uint32_t wlo,
+                                              uint32_t whi, int32_t* stats, uint32_t& k0, uint32_t& k1) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) atomicAdd(&stats[4], 1);
+  uint32_t* bmin = hist + kHistWords;  // (the collect columns of the warp: idle here)
+  uint32_t* bmax = bmin + 256;
+  const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+  const int x0 = i0.z, y0 = i0.w, x1 = i1.x, h = i1.y - y0 + 1;
+  const float* fbase = depth + (size_t)i0.y * H * W;
+  const int xa = x0 & ~3, Q = (x1 - xa + 4) >> 2;
+  const int P = i1.z & 0xfff, Qp = (i1.z >> 12) & 0xff, RPq = i1.z >> 20, nsteps = i1.w;
+  const int lr = (lane * (int)kRecip16[Qp]) >> 16, lq = lane - lr * Qp;
+  const bool active = lr < RPq;
+  const uint32_t rstep = (uint32_t)(RPq * W);
+  auto walk = [&](auto&& fn) {  // fn(key) for every valid key this lane owns
+    for (int p = 0; p < P; ++p) {
+      const int qq = p * Qp + lq;
+      const bool lane_ok = active && qq < Q;
+      const int col0 = xa + 4 * (lane_ok ? qq : 0);
+      uint32_t dm[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = (lane_ok && col0 + j >= x0 && col0 + j <= x1) ? dmax_bits : 0u;
+      const int row_l = lane_ok ? lr : 0;
+      const float* gp = fbase + (uint32_t)((y0 + row_l) * W + col0);
+#pragma unroll 1
+      for (int st = 0; st < nsteps; st += 4) {  // four row steps in flight: the walk is latency-bound (few warps run here)
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          q[u] = make_uint4(0u, 0u, 0u, 0u);
+          if ((st + u) * RPq + row_l < h) q[u] = ldg_u4(gp + (size_t)u * rstep);
+        }
+        gp += 4 * (size_t)rstep;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t bits[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (key_valid(bits[j], dm[j])) fn(bits[j]);
+        }
+      }
+    }
+  };
+  const int r1 = r + (two ? 1 : 0);
+  int below = -1;  // keys under the window: unknown for the caller's hint, counted by the first walk
+  while (true) {
+    if (wlo >= whi && below >= 0) { k0 = k1 = wlo; return; }
+    const uint32_t span = whi - wlo;
+    const int shift = max(0, 24 - __clz(span));  // (span >> shift) <= 255
+    if (lane == 0) atomicAdd(&stats[5], 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { hist[i * 32 + lane] = 0u; bmin[i * 32 + lane] = 0xffffffffu; bmax[i * 32 + lane] = 0u; }
+    __syncwarp();
+    int nb = 0;
+    walk([&](uint32_t k) {
+      const uint32_t d = k - wlo;
+      if (k < wlo) ++nb;
+      else if (d <= span) {
+        const uint32_t bin = d >> shift;
+        atomicAdd(&hist[bin], 1u);
+        atomicMin(&bmin[bin], k);
+        atomicMax(&bmax[bin], k);
+      }
+    });
+    __syncwarp();
+    if (below < 0) below = warp_sum_i(nb);
+    int b_lo = -1, b_hi = -1, before = 0, end = 0;
+    {
+      const uint4 h0 = reinterpret_cast<const uint4*>(hist)[2 * lane], h1 = reinterpret_cast<const uint4*>(hist)[2 * lane + 1];
+      const int c[8] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+      int tot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot += c[i];
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int cum = below + incl - tot;
+      int my_lo = -1, my_hi = -1, my_before = 0, my_end = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r >= cum && r < cum + c[i]) { my_lo = lane * 8 + i; my_before = cum; }
+        if (r1 >= cum && r1 < cum + c[i]) { my_hi = lane * 8 + i; my_end = cum + c[i]; }
+        cum += c[i];
+      }
+      const uint32_t m_lo = __ballot_sync(kFull, my_lo >= 0), m_hi = __ballot_sync(kFull, my_hi >= 0);
+      if (!m_lo || !m_hi) {  // the hint did not hold both ranks: start over on the full key range
+        wlo = 1u; whi = kKeyMaxValid; below = 0;
+        __syncwarp();
+        continue;
+      }
+      b_lo = __shfl_sync(kFull, my_lo, __ffs(m_lo) - 1);
+      before = __shfl_sync(kFull, my_before, __ffs(m_lo) - 1);
+      b_hi = __shfl_sync(kFull, my_hi, __ffs(m_hi) - 1);
+      end = __shfl_sync(kFull, my_end, __ffs(m_hi) - 1);
+    }
+    const uint32_t mn_lo = bmin[b_lo], mx_lo = bmax[b_lo], mn_hi = bmin[b_hi];
+    __syncwarp();
+    if (b_lo != b_hi) { k0 = mx_lo; k1 = mn_hi; return; }  // r is the largest key of its bin, r + 1 the smallest of the next
+    if (mn_lo >= mx_lo) { k0 = k1 = mn_lo; return; }      // one key value holds both ranks
+    const int cnt = end - before;
+    if (cnt <= kCollCap) {
+      if (lane == 0) hist[256] = 0u;
+      __syncwarp();
+      walk([&](uint32_t k) {
+        if ((k - mn_lo) <= (mx_lo - mn_lo)) {
+          const uint32_t pos = atomicAdd(&hist[256], 1u);
+          if (pos < (uint32_t)kCollCap) hist[pos] = k;
+        }
+      });
+      __syncwarp();
+      warp_select_hist(hist, cnt, r - before, two, lane, mn_lo, mx_lo, k0, k1);
+      return;
+    }
+    below = before; wlo = mn_lo; whi = mx_lo;
+  }
+}
+
 __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_kernel(const LiftArgs A) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1915,12 +2049,15 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
         }
         if (done) break;
 
-        // ---- not resolved: correct the window, or give up after two refinements -----------------------
+        // ---- not resolved.  A bracket that missed the rank is corrected and the histogram pass repeated, twice at
+        //      most.  Overfull bins / columns (ties, quantised depth, a very narrow mode) and everything else are
+        //      DEFERRED to lift_resolve_kernel: the record is written with a placeholder depth, the item goes on a
+        //      list together with a key window for the ranks (the span of the target bins + one bin either side). -----
         bool refine = attempt < 2 && s4f > 0.f;
         if (refine) {
           if (overfull) {  // span of the target bins plus one bin of margin either side
             const float nlo = wlo_f + (4.f * (float)(b_lo - 35) - 4.f) / s4f, nhi = wlo_f + (4.f * (float)(b_hi - 35) + 4.f) / s4f;
-            refine = (nhi - nlo) < 0.5f * (whi_f - wlo_f);  // (else: ties the map cannot split)
+            refine = attempt == 0 && (nhi - nlo) < 0.5f * (whi_f - wlo_f);  // (a second overfull window: ties, for the exact select)
             wlo_f = fmaxf(nlo, 1e-30f); whi_f = fmaxf(nhi, wlo_f);
           } else if (miss_low) {  // rank below the bracket: the side [lo/2, lo] (+ 5 bins of overlap: r+1 may sit just inside)
             const float ov = 0.02f * (whi_f - wlo_f);
@@ -1934,11 +2071,10 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
         if (refine) {
           set_map();
         } else {
-          SelWindow win;
-          win.wlo = 1u; win.whi = kKeyMaxValid; win.below = 0; win.cnt = n_valid_box;
-          win.straddle = false; win.split = 0u;
-          warp_select_global(fbase, W, rc, A.dmax_bits, lane, hist, kCollCap, win, r, two, A.counters, k0, k1);
-          __syncwarp();
+          if (lane == 0) {
+            const int slot = atomicAdd(&A.counters[10], 1);
+            reinterpret_cast<int4*>(A.deferred)[slot] = make_int4(item, __float_as_int(wlo_f), __float_as_int(whi_f), 0);
+          }
           done = true;
         }
       }
@@ -1955,6 +2091,41 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
       __syncwarp();
     }
     item_next = __shfl_sync(kFull, item_next, 0);
+  }
+}
+
+// lift_resolve_kernel: finishes the boxes lift_quad_kernel deferred (one warp per box, persistent).  Everything
+// but the percentile depth is already in the record; this kernel selects the two order statistics exactly
+// (quad_select_exact) and rewrites the words that depend on them: the four corners, the depth, the order stats.
+__global__ void __launch_bounds__(kQuadWarps * 32) lift_resolve_kernel(const LiftArgs A) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* hist = smem_u32 + wib * kHistWarpWords;
+  const int n = A.counters[10];
+  const WorkItem* __restrict__ items = reinterpret_cast<const WorkItem*>(A.items);
+  for (int i = blockIdx.x * kQuadWarps + wib; i < n; i += gridDim.x * kQuadWarps) {
+    const int4 d = reinterpret_cast<const int4*>(A.deferred)[i];
+    const int4* ip = reinterpret_cast<const int4*>(items + d.x);
+    const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+    const int b = i0.x;
+    float* outw = reinterpret_cast<float*>(A.out + b);
+    const int n_valid = __float_as_int(outw[22]);
+    int r = 0; bool two = false; double gamma = 0.0;
+    order_ranks(n_valid, A.quant, r, two, gamma);
+    uint32_t k0 = 0u, k1 = 0u;
+    quad_select_exact(A.depth, ip, A.H, A.W, A.dmax_bits, hist, r, two, (uint32_t)d.y, (uint32_t)d.z, A.counters, k0, k1);
+    __syncwarp();
+    if (lane == 0) {
+      const float4* tp = reinterpret_cast<const float4*>(ip + 2);
+      const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+      FrameTab tb;
+      tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
+      tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
+      tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+      write_record_depth_f32(outw, A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr, tb, i0.z, i0.w, i1.x, i1.y, k0, k1,
+                             (float)gamma, (float)(1.0 / A.scale_depth));
+    }
+    __syncwarp();
   }
 }
 
@@ -2760,6 +2931,8 @@ static int device_info(DeviceInfo** out) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.hist_ctas, lift_hist_kernel, kHistWarps * 32, kHistWarps * kHistWarpWords * 4);
     if (e != cudaSuccess) return (int)e;
     d.hist_ctas = std::max(d.hist_ctas, 1);
+    e = cudaFuncSetAttribute(lift_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadWarps * kHistWarpWords * 4);
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(lift_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadWarps * kQuadWarpWords * 4);
     if (e != cudaSuccess) return (int)e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.quad_ctas, lift_quad_kernel, kQuadWarps * 32, kQuadWarps * kQuadWarpWords * 4);
@@ -2957,7 +3130,7 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   prof_mark(2, st);
   LiftArgs A;
   A.depth = depth; A.rect4 = rect4; A.box_frame = ws.box_frame; A.tab = ws.tab;
-  A.counters = ws.counters; A.H = H; A.W = W;
+  A.counters = ws.counters; A.deferred = ws.deferred; A.H = H; A.W = W;
   A.dmax_bits = dmax_to_bits(max_depth_mm);
   A.quant = q_percent / 100.0;
   A.scale_depth = scale_depth;
@@ -2984,6 +3157,10 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
     } else if (warp_path() == kPathQuad && (W & 3) == 0) {
       const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->quad_ctas));
       lift_quad_kernel<<<grid, kQuadWarps * 32, kQuadWarps * kQuadWarpWords * 4, st>>>(A);
+      // the boxes it deferred (ties / quantised depth / bracket misses; none to a few per mille on continuous depth)
+      lift_resolve_kernel<<<(unsigned)std::min<int64_t>((B + kQuadWarps - 1) / kQuadWarps, (int64_t)dev->sms * 5), kQuadWarps * 32,
+                            kQuadWarps * kHistWarpWords * 4, st>>>(A);
+      g_launches += 1;
     } else {
       const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->hist_ctas));
       lift_hist_kernel<<<grid, kHistWarps * 32, kHistWarps * kHistWarpWords * 4, st>>>(A);

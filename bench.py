@@ -361,7 +361,8 @@ def run_lm3d(args):
         kern += np.array(list(ms4))
     lib.lm3d_profile_enable(0)
     kern /= reps
-    # rare-path counters of the last call (workspace words 4..6): fallbacks, narrowing passes, overflows
+    # rare-path counters of the last call (workspace words 4..6): exact selects (generic fallbacks; on the quad path
+    # the boxes deferred to lift_resolve_kernel), histogram passes beyond the first, candidate overflows
     rare = [int(v) for v in plan.workspace[:64].view(torch.int32)[4:7].cpu()]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

@@ -1,4 +1,6 @@
 """GPU parity: the CUDA path, called through the C ABI, against the numpy oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -165,6 +167,44 @@ def test_ties_and_constant_planes(cuda_device):
     # frame_off is uniform: 4 rects per frame
     for q in (50.0, 33.0):
         _rect_case(cuda_device, depth, rects, q=q)
+
+
+@pytest.mark.parametrize("step_mm", [1.0, 10.0, 250.0])
+def test_quantised_depth(cuda_device, step_mm):
+    """Depth rounded to a grid (sensor quantisation): the percentile bins hold runs of equal keys, up to whole boxes on
+    one value -- the boxes the histogram map cannot split (deferred to the exact key-space select of
+    lift_resolve_kernel on the quad path) must stay bit-exact."""
+    from lm3d import synth
+
+    seq = synth.make_sequence(6, 256, 192, 14, seed=21)
+    d = seq.depth
+    q = np.round(d / step_mm) * step_mm
+    seq.depth[...] = np.where(np.isfinite(d) & (d > 0), q, d).astype(np.float32)
+    rec, os_, rect4 = run_cuda(seq, cuda_device)
+    assert_records_match(rec, os_, run_oracle(seq, rect4))
+    rec, os_, rect4 = run_cuda(seq, cuda_device, q=25.0)
+    assert_records_match(rec, os_, run_oracle(seq, rect4, q=25.0))
+
+
+def test_quantised_depth_takes_the_exact_select(cuda_device):
+    """The case above must really exercise the exact select (workspace counter 4), not pass because the fast path
+    happened to cope: 250 mm steps put hundreds of equal keys in the percentile bin of most boxes."""
+    from lm3d import lift, synth
+
+    seq = synth.make_sequence(6, 256, 192, 14, seed=21)
+    d = seq.depth
+    seq.depth[...] = np.where(np.isfinite(d) & (d > 0), np.round(d / 250.0) * 250.0, d).astype(np.float32)
+    dev = cuda_device
+    fo = torch.from_numpy(seq.frame_off()).to(dev)
+    rect4 = lift.scale_boxes(torch.from_numpy(seq.boxes.reshape(-1, 4)).to(dev), torch.from_numpy(seq.image_wh()).to(dev), fo,
+                             seq.depth_width, seq.depth_height)
+    plan = lift.LiftPlan(seq.depth.shape[0], rect4.shape[0], dev, True)
+    rec, os_ = lift.lift_boxes(torch.from_numpy(seq.depth).to(dev), torch.from_numpy(seq.pose7).to(dev),
+                               torch.from_numpy(seq.intr4_depth_res()).to(dev), rect4, fo, plan=plan)
+    torch.cuda.synchronize()
+    if os.environ.get("LM3D_WARP_PATH", "quad") == "quad":
+        assert int(plan.workspace[:64].view(torch.int32)[4].cpu()) > 0, "no box took the exact select"
+    assert_records_match(lift.records_to_numpy(rec), os_.cpu().numpy(), run_oracle(seq, rect4.cpu().numpy()))
 
 
 def test_out_of_range_rects_are_clamped(cuda_device):
