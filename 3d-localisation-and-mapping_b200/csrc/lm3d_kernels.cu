@@ -2875,7 +2875,8 @@ __global__ void __launch_bounds__(256) ingest_depth_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_lm3d_launches{0};  // shared with lm3d_nms.cu
+static std::atomic<int64_t>& g_launches = g_lm3d_launches;
 
 // Optional per-kernel timing of lm3d_lift_boxes (bench.py's roofline leg): when enabled, six
 // events bracket the five kernels on the caller's stream.  Not thread-safe; off by default.
@@ -3030,6 +3031,7 @@ const char* lm3d_status_string(int s) {
     case LM3D_OK: return "ok";
     case LM3D_ERR_BAD_ARG: return "bad argument";
     case LM3D_ERR_WORKSPACE: return "workspace too small";
+    case LM3D_ERR_INTERNAL: return "internal invariant violated";
     case LM3D_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
     case LM3D_ERR_NO_DEVICE: return "no sm_100 CUDA device";
     case LM3D_ERR_TOO_LARGE: return "problem exceeds int32 indexing limits";

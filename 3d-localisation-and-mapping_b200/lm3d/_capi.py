@@ -25,6 +25,8 @@ SYMBOLS = (
     "lm3d_lift_frame_cloud",
     "lm3d_ingest_depth",
     "lm3d_lift_boxes_host",
+    "lm3d_nms_workspace_bytes",
+    "lm3d_nms_boxes",
     "lm3d_kernel_launches",
     "lm3d_profile_enable",
     "lm3d_profile_read",
@@ -75,6 +77,10 @@ def load():
     lib.lm3d_ingest_depth.argtypes = [vp, i64, C.c_float, vp, vp]
     lib.lm3d_lift_boxes_host.restype = C.c_int
     lib.lm3d_lift_boxes_host.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, C.c_int]
+    lib.lm3d_nms_workspace_bytes.restype = sz
+    lib.lm3d_nms_workspace_bytes.argtypes = [i64]
+    lib.lm3d_nms_boxes.restype = C.c_int
+    lib.lm3d_nms_boxes.argtypes = [vp, i64, vp, vp, i64, C.c_float, C.c_float, vp, vp, C.POINTER(C.c_int32), vp, sz, vp]
     lib.lm3d_kernel_launches.restype = i64
     lib.lm3d_kernel_launches.argtypes = []
     lib.lm3d_profile_enable.restype = C.c_int

@@ -32,7 +32,8 @@ typedef enum {
   LM3D_ERR_WORKSPACE = -2,    /* workspace_bytes < lm3d_workspace_bytes(F, B)           */
   LM3D_ERR_ALIGNMENT = -3,    /* depth / out / workspace not 16-byte aligned            */
   LM3D_ERR_NO_DEVICE = -4,    /* no CUDA device / wrong architecture (needs sm_100)     */
-  LM3D_ERR_TOO_LARGE = -5     /* H*W or B exceeds int32 indexing limits                 */
+  LM3D_ERR_TOO_LARGE = -5,    /* H*W or B exceeds int32 indexing limits                 */
+  LM3D_ERR_INTERNAL = -6      /* an invariant of the library did not hold (a bug)       */
 } lm3d_status;
 
 /* One record per box, 96 bytes.  Replaces the per-box result assembled at
@@ -103,6 +104,25 @@ int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, c
  *   depth_out [n_pixels] f32 = fp32(raw) * scale, computed in fp32 like the reference (scale = 1000);
  *             may alias raw_8uc4 (in place)                                                          */
 int lm3d_ingest_depth(const void* raw_8uc4, int64_t n_pixels, float scale, float* depth_out, void* stream);
+
+/* 3-D non-maximum suppression over lifted boxes: replaces BoundingBoxProcessor(global_bboxes_data,
+ * pose_df).suppress_bboxes() (task_def.py:145-149; the class's source, src/mapper/bbox_optimiser.py, is not in the
+ * reference repository, so the rules are DEFINED: NMS-SPEC v0 in oracle/nms_numpy.py / DESIGN.md 4.8).
+ *   corners   [B] x 12 floats (four world XYZ corners, the first 12 floats of a record), stride_floats apart:
+ *             pass the lm3d_box_out array with stride_floats = 24, or a packed [B,12] array with 12
+ *   conf      [B] f32 detector confidence;  label [B] i32 class id (only equal labels compete)
+ *   extent of a box = bounds of its corners grown by pad_m on every side; boxes with a non-finite corner or
+ *   confidence do not take part; two boxes overlap iff IoU_3D > iou_thr; greedy in confidence order (ties: lower
+ *   index first)
+ *   keep      [B] u8: 1 = kept;  parent [B] i32 (may be NULL): own index if kept, the kept box that suppressed it,
+ *             -1 if the box does not take part
+ *   rounds_out (HOST pointer, may be NULL): relaxation rounds launched
+ * Unlike the lift, this call SYNCHRONISES the stream (one 4-byte readback per batch of rounds decides whether
+ * another batch is needed).  Workspace: lm3d_nms_workspace_bytes(B), 16-byte aligned.                          */
+size_t lm3d_nms_workspace_bytes(int64_t B);
+int lm3d_nms_boxes(const float* corners, int64_t stride_floats, const float* conf, const int32_t* label, int64_t B,
+                   float iou_thr, float pad_m, uint8_t* keep, int32_t* parent, int32_t* rounds_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* Host-buffer convenience for bindings without a device allocator (the e2e path): copies the
  * sequence to the device in frame chunks on two streams (copy overlapped with compute), runs
