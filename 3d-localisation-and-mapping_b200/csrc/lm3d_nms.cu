@@ -139,10 +139,13 @@ __device__ __forceinline__ uint32_t bucket_of(int x, int y, int z, uint32_t mask
 
 // 1. extents (N1, N2), grid bounds
 __global__ void nms_extents_kernel(const float* __restrict__ corners, int64_t stride, const float* __restrict__ conf,
-                                   const int32_t* __restrict__ label, int64_t B, float pad, Workspace ws) {
+                                   const int32_t* __restrict__ label, int64_t B, float pad, uint8_t* __restrict__ keep,
+                                   int32_t* __restrict__ parent, Workspace ws) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float cx = INFINITY, cy = INFINITY, cz = INFINITY, ext = 0.f;
   if (i < B) {
+    keep[i] = 0;  // boxes that do not take part (N2) never reach the bucket-ordered arrays: their results are final here
+    if (parent) parent[i] = -1;
     const float* c = corners + i * stride;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     bool ok = true;
@@ -221,14 +224,18 @@ __global__ void nms_scatter_kernel(int64_t B, Workspace ws) {
   ws.state[p] = kUndecided;
 }
 
-// One warp walks the same-label overlapping predecessors of the box at bucket-ordered position p, 32 candidates
-// at a time: fn(q, is_rival) is called by every lane (q = candidate position, or -1 past the end of a bucket) and
-// returns true (warp-uniform) to end the walk.
-template <typename Fn>
-__device__ __forceinline__ void warp_for_each_rival(int p, int lane, const Workspace& ws, const Grid& g, float thr, Fn&& fn) {
+// One warp walks the candidates of the box at bucket-ordered position p, 32 at a time.  Every lane first reads
+// the candidate's STATE (4 coalesced bytes) and asks want(state) whether the candidate matters at all -- suppressed
+// boxes never do, undecided ones only until the box is known to be blocked -- before it pays for the 36 bytes of
+// the overlap test.  fn(state, is_rival) is then called by every lane (state = kSuppressed for lanes past the end
+// of a bucket) and returns true (warp-uniform) to end the walk.
+template <typename Want, typename Fn>
+__device__ __forceinline__ void warp_for_each_rival(int p, int lane, const Workspace& ws, const Grid& g, float thr,
+                                                    Want&& want, Fn&& fn) {
   const float4 lo = ws.lo_conf[p], hi = ws.hi_label[p];
   const float vol = ws.vol[p];
   const int me = ws.idx[p];
+  const volatile int32_t* state = ws.state;
   int x, y, z;
   cell_xyz(lo, hi, g, x, y, z);
   int2 hdr = make_int2(0, 0);
@@ -237,32 +244,40 @@ __device__ __forceinline__ void warp_for_each_rival(int p, int lane, const Works
     const int n = __shfl_sync(0xffffffffu, hdr.x, c), start = __shfl_sync(0xffffffffu, hdr.y, c);
     for (int base = 0; base < n; base += 32) {
       const int q = (base + lane < n) ? start + base + lane : -1;
+      int sq = kSuppressed;
       bool rival = false;
       if (q >= 0 && q != p) {
-        const float4 lo_q = ws.lo_conf[q], hi_q = ws.hi_label[q];
-        rival = __float_as_int(hi_q.w) == __float_as_int(hi.w) && precedes(lo_q.w, ws.idx[q], lo.w, me) &&
-                overlaps(lo, hi, vol, lo_q, hi_q, ws.vol[q], thr);
+        sq = state[q];
+        if (want(sq)) {
+          const float4 lo_q = ws.lo_conf[q], hi_q = ws.hi_label[q];
+          rival = __float_as_int(hi_q.w) == __float_as_int(hi.w) && precedes(lo_q.w, ws.idx[q], lo.w, me) &&
+                  overlaps(lo, hi, vol, lo_q, hi_q, ws.vol[q], thr);
+        }
       }
-      if (fn(q, rival)) return;
+      if (fn(q, sq, rival)) return;
     }
   }
 }
 
 // 5. one relaxation round (in place), one warp per box
-__global__ void nms_round_kernel(int n_boxes, float thr, int round, Workspace ws) {
+__global__ void nms_round_kernel(float thr, int round, Workspace ws) {
   if (round > 0 && ws.hdr->remaining[(round - 1) % kMaxRoundSlots] == 0) return;  // converged in an earlier round
   const int lane = threadIdx.x & 31;
   const int p = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (p >= n_boxes || ws.state[p] != kUndecided) return;
+  if (p >= ws.hdr->cursor || ws.state[p] != kUndecided) return;
   const Grid g = load_grid(ws.hdr, (uint32_t)(ws.buckets - 1));
-  const volatile int32_t* state = ws.state;
   bool suppressed = false, blocked = false;
-  warp_for_each_rival(p, lane, ws, g, thr, [&](int q, bool rival) {
-    const int s = rival ? state[q] : kSuppressed;
-    if (__any_sync(0xffffffffu, s == kKept)) { suppressed = true; return true; }
-    blocked = blocked || __any_sync(0xffffffffu, s == kUndecided);
-    return false;
-  });
+  warp_for_each_rival(
+      p, lane, ws, g, thr,
+      // a KEPT candidate can suppress the box; an UNDECIDED one can only block it, which needs finding once
+      [&](int s) { return s == kKept || (s == kUndecided && !blocked); },
+      [&](int, int s, bool rival) {
+        if (__any_sync(0xffffffffu, rival && s == kKept)) { suppressed = true; return true; }
+        blocked = blocked || __any_sync(0xffffffffu, rival && s == kUndecided);
+        // round 0 starts with nothing KEPT: a blocked box cannot be decided by this walk (short of a rival decided
+        // while it runs), so it stops here; only the local maxima scan all their candidates
+        return round == 0 && blocked;
+      });
   if (lane == 0) {
     if (suppressed) ws.state[p] = kSuppressed;
     else if (!blocked) ws.state[p] = kKept;
@@ -271,11 +286,10 @@ __global__ void nms_round_kernel(int n_boxes, float thr, int round, Workspace ws
 }
 
 // 6. results in input order: keep flags and the suppressing box (the first KEPT rival in greedy order)
-__global__ void nms_finish_kernel(int n_boxes, float thr, uint8_t* __restrict__ keep, int32_t* __restrict__ parent,
-                                  Workspace ws) {
+__global__ void nms_finish_kernel(float thr, uint8_t* __restrict__ keep, int32_t* __restrict__ parent, Workspace ws) {
   const int lane = threadIdx.x & 31;
   const int p = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (p >= n_boxes) return;
+  if (p >= ws.hdr->cursor) return;
   const int s = ws.state[p], me = ws.idx[p];
   if (lane == 0) keep[me] = (s == kKept) ? 1 : 0;
   if (!parent) return;
@@ -283,8 +297,8 @@ __global__ void nms_finish_kernel(int n_boxes, float thr, uint8_t* __restrict__ 
   if (s == kSuppressed) {
     const Grid g = load_grid(ws.hdr, (uint32_t)(ws.buckets - 1));
     float best_conf = 0.f;
-    warp_for_each_rival(p, lane, ws, g, thr, [&](int q, bool rival) {
-      if (rival && ws.state[q] == kKept) {
+    warp_for_each_rival(p, lane, ws, g, thr, [](int sq) { return sq == kKept; }, [&](int q, int, bool rival) {
+      if (rival) {
         const int j = ws.idx[q];
         const float cj = ws.lo_conf[q].w;
         if (best < 0 || precedes(cj, j, best_conf, best)) { best = j; best_conf = cj; }
@@ -299,14 +313,6 @@ __global__ void nms_finish_kernel(int n_boxes, float thr, uint8_t* __restrict__ 
     }
   }
   if (lane == 0) parent[me] = best;
-}
-
-// boxes that do not take part (N2) never reach the bucket-ordered arrays
-__global__ void nms_init_out_kernel(int64_t B, uint8_t* __restrict__ keep, int32_t* __restrict__ parent) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  keep[i] = 0;
-  if (parent) parent[i] = -1;
 }
 
 }  // namespace lm3d_nms
@@ -344,19 +350,12 @@ int lm3d_nms_boxes(const float* corners, int64_t stride_floats, const float* con
   e = cudaMemsetAsync(ws.bucket, 0, (size_t)ws.buckets * 8, st);
   if (e != cudaSuccess) return (int)e;
   const unsigned grid = (unsigned)((B + 255) / 256);
-  nms_init_out_kernel<<<grid, 256, 0, st>>>(B, keep, parent);
-  nms_extents_kernel<<<grid, 256, 0, st>>>(corners, stride_floats, conf, label, B, pad_m, ws);
+  nms_extents_kernel<<<grid, 256, 0, st>>>(corners, stride_floats, conf, label, B, pad_m, keep, parent, ws);
   nms_assign_kernel<<<grid, 256, 0, st>>>(B, ws);
   nms_ranges_kernel<<<(unsigned)((ws.buckets + 255) / 256), 256, 0, st>>>(ws);
   nms_scatter_kernel<<<grid, 256, 0, st>>>(B, ws);
-  g_lm3d_launches += 5;
-  int32_t n_boxes = 0;  // boxes that take part = length of the bucket-ordered arrays
-  e = cudaMemcpyAsync(&n_boxes, &ws.hdr->cursor, 4, cudaMemcpyDeviceToHost, st);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return (int)e;
-  if (n_boxes == 0) return (int)cudaGetLastError();
-  const unsigned wgrid = (unsigned)(((int64_t)n_boxes * 32 + 255) / 256);  // one warp per box
+  g_lm3d_launches += 4;
+  const unsigned wgrid = (unsigned)((B * 32 + 255) / 256);  // one warp per box (boxes taking part: hdr->cursor <= B)
   int round = 0;
   while (true) {
     for (int k = 0; k < kRoundsPerBatch; ++k, ++round) {
@@ -364,7 +363,7 @@ int lm3d_nms_boxes(const float* corners, int64_t stride_floats, const float* con
         e = cudaMemsetAsync(&ws.hdr->remaining[round % kMaxRoundSlots], 0, 4, st);
         if (e != cudaSuccess) return (int)e;
       }
-      nms_round_kernel<<<wgrid, 256, 0, st>>>(n_boxes, iou_thr, round, ws);
+      nms_round_kernel<<<wgrid, 256, 0, st>>>(iou_thr, round, ws);
     }
     g_lm3d_launches += kRoundsPerBatch;
     int32_t remaining = 0;
@@ -376,7 +375,7 @@ int lm3d_nms_boxes(const float* corners, int64_t stride_floats, const float* con
     if (round > B + kRoundsPerBatch) return LM3D_ERR_INTERNAL;  // (cannot happen: every round decides >= 1 box)
   }
   if (rounds_out) *rounds_out = round;
-  nms_finish_kernel<<<wgrid, 256, 0, st>>>(n_boxes, iou_thr, keep, parent, ws);
+  nms_finish_kernel<<<wgrid, 256, 0, st>>>(iou_thr, keep, parent, ws);
   g_lm3d_launches += 1;
   return (int)cudaGetLastError();
 }
