@@ -57,6 +57,26 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert lib.lm3d_kernel_launches() == 0
 
 
+def test_nms_argument_validation(lib):
+    z = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)          # any non-null, 16-byte aligned value: rejected before it is dereferenced
+    r = ctypes.c_int32(7)
+    f = ctypes.c_float
+    assert lib.lm3d_nms_workspace_bytes(-1) == 0
+    w1, w2 = lib.lm3d_nms_workspace_bytes(100), lib.lm3d_nms_workspace_bytes(200000)
+    assert 0 < w1 < w2 and w2 % 256 == 0
+    assert lib.lm3d_nms_boxes(z, 24, z, z, 0, f(0.1), f(0.03), z, z, ctypes.byref(r), z, 0, z) == 0 and r.value == 0  # B == 0
+    assert lib.lm3d_nms_boxes(one, 24, one, one, -1, f(0.1), f(0.03), one, z, None, one, 1 << 20, z) == -1
+    assert lib.lm3d_nms_boxes(one, 11, one, one, 5, f(0.1), f(0.03), one, z, None, one, 1 << 20, z) == -1   # stride < 12
+    assert lib.lm3d_nms_boxes(one, 24, one, one, 5, f(-0.1), f(0.03), one, z, None, one, 1 << 20, z) == -1  # thr < 0
+    assert lib.lm3d_nms_boxes(one, 24, one, one, 5, f(float("nan")), f(0.03), one, z, None, one, 1 << 20, z) == -1
+    assert lib.lm3d_nms_boxes(z, 24, one, one, 5, f(0.1), f(0.03), one, z, None, one, 1 << 20, z) == -1     # null corners
+    assert lib.lm3d_nms_boxes(one, 24, one, one, 5, f(0.1), f(0.03), one, z, None, ctypes.c_void_p(24), 1 << 20, z) == -3
+    assert lib.lm3d_nms_boxes(one, 24, one, one, 5, f(0.1), f(0.03), one, z, None, one, 64, z) == -2        # workspace too small
+    assert b"invariant" in lib.lm3d_status_string(-6)
+    assert lib.lm3d_kernel_launches() == 0
+
+
 def test_no_cpu_fallback_when_library_missing(monkeypatch, tmp_path):
     from lm3d import _capi
 
