@@ -415,6 +415,40 @@ __device__ __forceinline__ void sample_bracket_regs(const float* __restrict__ fb
   if (b < sv) hi = sb;
 }
 
+// Same, and also the sample values at the target rank -/+ zc sigma (zc < z): the capture window of lift_quad_kernel.
+template <int E>
+__device__ __forceinline__ void sample_bracket_regs2(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                     uint32_t dmax_bits, double quant, float z, float zc, int lane,
+                                                     uint32_t& lo, uint32_t& hi, uint32_t& clo, uint32_t& chi) {
+  uint32_t s[E];
+  int sv = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    const int ic = i & 7, ir = i >> 3;
+    const int cx = ((2 * ic + 1) * rc.w) >> 4;
+    const int ry = ((2 * ir + 1) * rc.h) / (8 * E);
+    const uint32_t bits = __float_as_uint(__ldg(fbase + (uint32_t)((rc.y0 + ry) * W + rc.x0 + cx)));
+    const bool v = key_valid(bits, dmax_bits);
+    s[e] = v ? bits : kKeyInvalid;
+    sv += v;
+  }
+  sv = warp_sum_i(sv);
+  if (sv == 0) return;
+  warp_bitonic<E>(s, lane);
+  int a, b, ca, cb;
+  bracket_ranks(sv, quant, z, a, b);
+  bracket_ranks(sv, quant, zc, ca, cb);
+  const uint32_t sa = warp_sorted_at<E>(s, max(a, 0));
+  const uint32_t sb = warp_sorted_at<E>(s, min(max(b, 0), 32 * E - 1));
+  const uint32_t sca = warp_sorted_at<E>(s, max(ca, 0));
+  const uint32_t scb = warp_sorted_at<E>(s, min(max(cb, 0), 32 * E - 1));
+  if (a >= 0) lo = sa;
+  if (b < sv) hi = sb;
+  if (ca >= 0) clo = sca;
+  if (cb < sv) chi = scb;
+}
+
 // The biggest warp boxes (5 % of config C2) take 256 samples through shared memory (the
 // candidate buffer is idle before the fused pass) and the rolled shared-memory sort: 17 %.
 __device__ __noinline__ void sample_bracket_smem(const float* __restrict__ fbase, int W, const Rect& rc,
@@ -1504,7 +1538,26 @@ constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane k
 #endif
 constexpr int kQuadDepth2 = LM3D_QUAD_DEPTH2;
 constexpr int kQuadSlotsMax = kQuadDepth > kQuadDepth2 ? kQuadDepth : kQuadDepth2;
-constexpr int kQuadWarpWords = kHistWarpWords + kQuadSlotsMax * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
+// LM3D_QUAD_CAPTURE (experiment, off): pass 1 also appends the keys of a CENTRAL window of bins (the sample's target
+// rank +- kCaptureZ sigma) to the lane-private columns; when the target bins turn out to lie inside it (and no
+// column ran over), pass 2 -- a second stream of the whole rect -- is skipped and the select works on the captured
+// keys.  Measured on C2: 214 instead of 180 SASS instructions per row-step pair in pass 1, pass 2 skipped for only
+// 52 % of the boxes (z = 1.25: 6 % had the target outside the window, 41 % overflowed a 44-deep column -- keys near
+// the median are spatially clustered, so a few lanes get most of them), 1.29 ms instead of 1.23 ms.  Narrower
+// (z = 0.75) and wider (z = 2) windows are no better (tools/capture_stats.py).  Kept for A/B builds only.
+#ifndef LM3D_QUAD_CAPTURE
+#define LM3D_QUAD_CAPTURE 0
+#endif
+#ifndef LM3D_QUAD_COLL_ROWS
+#define LM3D_QUAD_COLL_ROWS (LM3D_QUAD_CAPTURE ? 44 : 28)
+#endif
+#ifndef LM3D_CAPTURE_Z
+#define LM3D_CAPTURE_Z 1.25f
+#endif
+[[maybe_unused]] constexpr float kCaptureZ = LM3D_CAPTURE_Z;
+constexpr int kQuadCollRows = LM3D_QUAD_COLL_ROWS;            // private column depth per lane in lift_quad_kernel (+4 guard rows)
+constexpr int kQuadCollWords = 32 * (kQuadCollRows + 4);
+constexpr int kQuadWarpWords = kHistWords + kQuadCollWords + kQuadSlotsMax * 128;  // + a 512-byte slot (32 lanes x 16 B) per step in flight
 
 __constant__ uint32_t kRecip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,  // ceil(65536 / Qp)
                                       7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
@@ -1516,9 +1569,11 @@ struct AccQ {
 };
 
 // pass 1 on one quad (4 pixels of one row, columns col0 .. col0+3)
+template <bool CAP>
 __device__ __forceinline__ void accum_quad_hist(const uint4 q, const uint32_t (&dm)[4], float vr, float b0, float b1, float b2,
                                                 const f32x2 (&cA)[3], const f32x2 (&cB)[3], float s4f, float kkf, float ylo,
-                                                float yhi, uint32_t hist_bias, AccQ& A) {
+                                                float yhi, uint32_t hist_bias, AccQ& A, uint32_t cap_tgt, uint32_t cap_dt,
+                                                uint32_t& cptr) {
   const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
   bool v[4];
   uint32_t key[4];
@@ -1548,6 +1603,14 @@ __device__ __forceinline__ void accum_quad_hist(const uint4 q, const uint32_t (&
     const float yc = fminf(fmaxf(y[j], ylo), yhi);  // NaN -> ylo
     const uint32_t ad = __float_as_uint(yc) * 4u + hist_bias;
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(ad) : "memory");
+  }
+  // capture: keys whose histogram word lies in the central window go to the lane's private column (an invalid pixel
+  // carries y = NaN, whose bits are far above any window)
+  if constexpr (CAP) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("{\n.reg .pred p;\n.reg .b32 t;\nsub.u32 t, %2, %3;\nsetp.le.u32 p, t, %4;\n@p st.shared.u32 [%0], %1;\n@p add.u32 %0, %0, 128;\n}"
+                   : "+r"(cptr) : "r"(bits[j]), "r"(__float_as_uint(y[j])), "r"(cap_tgt), "r"(cap_dt) : "memory");
   }
 }
 
@@ -1713,7 +1776,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
   uint32_t hist_s, coll_s, pipe_s, lt_mask;
   asm volatile("mov.u32 %0, %1;" : "=r"(hist_s) : "r"((uint32_t)__cvta_generic_to_shared(hist)));
   asm volatile("mov.u32 %0, %1;" : "=r"(coll_s) : "r"((uint32_t)__cvta_generic_to_shared(hist + kHistWords) + (uint32_t)lane * 4));
-  asm volatile("mov.u32 %0, %1;" : "=r"(pipe_s) : "r"((uint32_t)__cvta_generic_to_shared(hist + kHistWarpWords) + (uint32_t)lane * 16));
+  asm volatile("mov.u32 %0, %1;" : "=r"(pipe_s) : "r"((uint32_t)__cvta_generic_to_shared(hist + kHistWords + kQuadCollWords) + (uint32_t)lane * 16));
   asm volatile("mov.u32 %0, %1;" : "=r"(lt_mask) : "r"(lanemask_lt()));
   const int n_items = A.counters[A.count_idx];
   const int W = A.W;
@@ -1739,8 +1802,15 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
 
       // ---- sample -> bracket -> histogram map ------------------------------------------------
       uint32_t lo = 1u, hi = kKeyMaxValid;
+#if LM3D_QUAD_CAPTURE
+      uint32_t clo = 0u, chi = 0xffffffffu;  // (no sample: the capture window is the whole bracket)
+      if (n_pix > 64) sample_bracket_regs2<LM3D_QUAD_SAMPLE_E>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, kCaptureZ, lane, lo, hi, clo, chi);
+      hi = min(hi, A.dmax_bits);
+      clo = max(clo, lo); chi = min(chi, hi);
+#else
       if (n_pix > 64) sample_bracket_regs<LM3D_QUAD_SAMPLE_E>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
       hi = min(hi, A.dmax_bits);
+#endif
       // the bracket as depths [wlo_f, whi_f]; 250 of the 256 bins span it (see 3b for the map)
       float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
       float s4f, kkf;
@@ -1750,6 +1820,16 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
         kkf = fmaf(-wlo_f, s4f, 33554432.f + 4.f * 35.f);
       };
       set_map();
+#if LM3D_QUAD_CAPTURE
+      // capture window as histogram words (bits of y): [cap_tgt, cap_tgt + cap_dt]
+      const uint32_t cap_tgt = __float_as_uint(fmaf(__uint_as_float(clo), s4f, kkf));
+      const uint32_t cap_dt = __float_as_uint(fmaf(__uint_as_float(max(chi, clo)), s4f, kkf)) - cap_tgt;
+      uint32_t cap_ptr = coll_s;
+      bool cap_live = true;  // the columns hold pass 1's capture (first attempt only)
+#else
+      const uint32_t cap_tgt = 0u, cap_dt = 0u;
+      uint32_t cap_ptr = 0u;
+#endif
       const float ylo = 33554432.f + 4.f * (float)lane, yhi = 33554432.f + 4.f * (float)(288 + lane);
       const uint32_t hist_bias = hist_s - 0x30000000u;
 #pragma unroll
@@ -1818,7 +1898,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
             const uint4 q0 = qa;
             qa = zq;
             if (nxt_row < rows_l) qa = ldg_u4(gp);
-            accum_quad_hist(q0, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc);
+            accum_quad_hist<LM3D_QUAD_CAPTURE != 0>(q0, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, cap_tgt, cap_dt, cap_ptr);
             vr += frp;
             if (st + 1 >= nsteps) break;
             const uint4 q1 = qb;
@@ -1826,7 +1906,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
             if (nxt_row + RPq < rows_l) qb = ldg_u4(gp + rstep);
             gp += 2 * rstep;
             nxt_row += 2 * RPq;
-            accum_quad_hist(q1, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc);
+            accum_quad_hist<LM3D_QUAD_CAPTURE != 0>(q1, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, cap_tgt, cap_dt, cap_ptr);
             vr += frp;
           }
 #else
@@ -1854,7 +1934,10 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
               cp_async_commit();
               gp += rstep;
               nxt_row += RPq;
-              accum_quad_hist(q0, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc);
+              accum_quad_hist<LM3D_QUAD_CAPTURE != 0>(q0, dm, vr, tb_b0, tb_b1, tb_b2, cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, cap_tgt, cap_dt, cap_ptr);
+#if LM3D_QUAD_CAPTURE
+              cap_ptr = min(cap_ptr, coll_s + kQuadCollRows * 128);
+#endif
               vr += frp;
             }
           }
@@ -1954,12 +2037,25 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
         const bool found = b_lo >= 32;
         bool overfull = found && n_coll > kCollCap;
 
+        bool have = false;  // the columns already hold every key of the target bins (captured by pass 1)
+#if LM3D_QUAD_CAPTURE
+        if (found && !overfull && cap_live) {
+          const uint32_t t_lo = 0x4C000000u + (uint32_t)b_lo, t_hi = 0x4C000000u + (uint32_t)b_hi;
+          have = (t_lo - cap_tgt) <= cap_dt && (t_hi - cap_tgt) <= cap_dt &&
+                 !__any_sync(kFull, cap_ptr >= coll_s + kQuadCollRows * 128);
+          if (have && lane == 0) atomicAdd(&A.counters[7], 1);
+#ifdef LM3D_DEBUG_REASONS
+          if (!have && lane == 0) atomicAdd(&A.counters[((t_lo - cap_tgt) <= cap_dt && (t_hi - cap_tgt) <= cap_dt) ? 13 : 12], 1);
+#endif
+        }
+        cap_live = false;
+#endif
         if (found && !overfull) {
           // ---- pass 2: re-read the rect (L2), keep the keys of the target bins in private columns ------
           const uint32_t tgt = 0x4C000000u + (uint32_t)b_lo, dt = (uint32_t)(b_hi - b_lo);
-          uint32_t cptr = coll_s;
-          const uint32_t cend = coll_s + kCollRows * 128;
-          for (int p = 0; p < P; ++p) {
+          uint32_t cptr = have ? cap_ptr : coll_s;
+          const uint32_t cend = coll_s + kQuadCollRows * 128;
+          for (int p = 0; p < (have ? 0 : P); ++p) {
             const int qq = p * Qp + lq;
             const bool lane_ok = active && qq < Q;
             const int col0 = xa + 4 * (lane_ok ? qq : 0);
@@ -2020,7 +2116,11 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
             int ncoll = 0;
             for (int row = 0; row < rows; ++row) {
               const uint32_t key = (row < cnt_l) ? coll[row * 32 + lane] : 0u;
+#if LM3D_QUAD_CAPTURE
+              const bool in = key_valid(key, A.dmax_bits) && (__float_as_uint(fmaf(__uint_as_float(key), s4f, kkf)) - tgt) <= dt;
+#else
               const bool in = key_valid(key, A.dmax_bits);
+#endif
               const uint32_t bal = __ballot_sync(kFull, in);
               const int pos = ncoll + __popc(bal & lt_mask);
               if (in && pos < kCollCap) hist[pos] = key;
@@ -2565,6 +2665,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
       const float* gp = fbase + (uint32_t)((rc.y0 + row_l) * W + col0);
       float vr = (float)(rc.y0 + row_l) - vc;
       const int rows_l = rc.h - row_l;
+      uint32_t no_cptr = 0u;
       acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
 #pragma unroll
       for (int i = 0; i < kQuadDepth; ++i) {
@@ -2584,7 +2685,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
           cp_async_commit();
           gp += rstep;
           nxt_row += RPq;
-          accum_quad_hist(q0, dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc);
+          accum_quad_hist<false>(q0, dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, 0u, 0u, no_cptr);
           vr += frp;
         }
       }

@@ -363,7 +363,7 @@ def run_lm3d(args):
     kern /= reps
     # rare-path counters of the last call (workspace words 4..6): exact selects (generic fallbacks; on the quad path
     # the boxes deferred to lift_resolve_kernel), histogram passes beyond the first, candidate overflows
-    rare = [int(v) for v in plan.workspace[:64].view(torch.int32)[4:7].cpu()]
+    rare = [int(v) for v in plan.workspace[:64].view(torch.int32)[4:8].cpu()]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -394,7 +394,8 @@ def run_lm3d(args):
         "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_tma": kern[2], "lift_warp": kern[3],
                       "lift_large": kern[4]},
         "warp_path": os.environ.get("LM3D_WARP_PATH", "quad"),
-        "rare_paths": {"global_fallbacks": rare[0], "narrowing_passes": rare[1], "candidate_overflows": rare[2]},
+        "rare_paths": {"global_fallbacks": rare[0], "narrowing_passes": rare[1], "candidate_overflows": rare[2],
+                       "pass2_skipped": rare[3]},
     }
 
     # ---- e2e: HOST buffers through lm3d_lift_boxes_host --------------------------------------
