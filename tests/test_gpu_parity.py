@@ -158,14 +158,17 @@ def test_widths_not_multiple_of_16_or_4(cuda_device):
 
 def test_ties_and_constant_planes(cuda_device):
     rng = np.random.default_rng(4)
-    depth = np.full((3, 256, 192), 1234.5, dtype=np.float32)           # constant plane
+    depth = np.full((4, 256, 192), 1234.5, dtype=np.float32)           # constant plane
     depth[1] = np.where(rng.random((256, 192)) < 0.5, 1000.0, 2000.0)  # two values
     depth[2] = np.round(1000 + 30 * rng.random((256, 192)))            # ~30 distinct values
+    depth[3, :, :96] = 1000.0                                          # two values, split down the middle: rects centred
+    depth[3, :, 96:] = 2000.0                                          # on x = 96 have the two median ranks on either side
     rects = []
     for f in range(3):
         rects += [(0, 0, 191, 255), (20, 30, 90, 140), (5, 5, 40, 40), (0, 0, 7, 7)]
+    rects += [(0, 0, 191, 255), (56, 10, 135, 49), (76, 100, 115, 139), (92, 7, 99, 14)]
     # frame_off is uniform: 4 rects per frame
-    for q in (50.0, 33.0):
+    for q in (50.0, 33.0, 0.0, 100.0):
         _rect_case(cuda_device, depth, rects, q=q)
 
 
