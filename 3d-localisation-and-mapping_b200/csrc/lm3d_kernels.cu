@@ -2904,12 +2904,18 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
 // ------------------------------------------------------------------------------------------
 // full-frame world cloud (next-row #3: pose_processor.py:154-156, 262-271)
 // ------------------------------------------------------------------------------------------
+constexpr int kCloudUnroll = 4;  // quads per lane in flight: a streaming kernel needs ~45 KB of loads in flight per SM
 __global__ void __launch_bounds__(256) frame_cloud_kernel(const float* __restrict__ depth, int64_t F, int H, int W,
                                                           const FrameTab* __restrict__ tab, uint32_t dmax_bits,
                                                           float* __restrict__ xyz, int32_t* __restrict__ n_valid) {
-  // grid.y = frame; each thread handles 4 consecutive pixels (float4 load, 3 float4 stores)
+  // grid.y = frame; per step a warp takes kCloudUnroll runs of 128 consecutive pixels: all its float4 loads are
+  // issued first, then each run is transformed and its 96 float4 of output (x, y, z interleaved) staged through
+  // shared memory so that every store instruction writes 512 contiguous bytes (a lane's own 12 floats sit 48
+  // bytes apart: three half-filled sectors per store otherwise)
+  __shared__ __align__(16) float stage[8][384];
   const int64_t f = blockIdx.y;
-  const int hw = H * W;
+  const int hw = H * W, lane = threadIdx.x & 31;
+  float* st = stage[threadIdx.x >> 5];
   const float* fb = depth + f * hw;
   float* ob = xyz + f * (int64_t)hw * 3;
   const float4* tp = reinterpret_cast<const float4*>(tab + f);
@@ -2917,42 +2923,70 @@ __global__ void __launch_bounds__(256) frame_cloud_kernel(const float* __restric
   const float a0 = t0.x, a1 = t0.y, a2 = t0.z, b0 = t0.w, b1 = t1.x, b2 = t1.y, c0 = t1.z, c1 = t1.w, c2 = t2.x,
               tx = t2.y, ty = t2.z, tz = t2.w;
   const float qnan = __uint_as_float(0x7fc00000u);
+  const bool vec = (hw & 3) == 0 && (W & 3) == 0;  // 4 pixels of a lane share a row, loads / stores are 16-byte aligned
+  const int warps = (gridDim.x * blockDim.x) >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int cnt = 0;
-  for (int p4 = blockIdx.x * blockDim.x + threadIdx.x; p4 * 4 < hw; p4 += gridDim.x * blockDim.x) {
-    const int p = p4 * 4;
-    float d[4];
-    if (p + 3 < hw && (hw & 3) == 0) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(fb + p));
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    } else {
+  for (int wp0 = warp * (128 * kCloudUnroll); wp0 < hw; wp0 += warps * (128 * kCloudUnroll)) {  // (warp-uniform)
+    float4 dq[kCloudUnroll];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) d[j] = (p + j < hw) ? __ldg(fb + p + j) : 0.f;
+    for (int k = 0; k < kCloudUnroll; ++k) {
+      const int p = wp0 + k * 128 + lane * 4;
+      dq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec) {
+        if (p < hw) dq[k] = __ldg(reinterpret_cast<const float4*>(fb + p));
+      } else {
+        if (p + 0 < hw) dq[k].x = __ldg(fb + p + 0);
+        if (p + 1 < hw) dq[k].y = __ldg(fb + p + 1);
+        if (p + 2 < hw) dq[k].z = __ldg(fb + p + 2);
+        if (p + 3 < hw) dq[k].w = __ldg(fb + p + 3);
+      }
     }
-    float o[12];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pp = p + j;
-      const int v = pp / W, u = pp - v * W;
-      const bool valid = key_valid(__float_as_uint(d[j]), dmax_bits) && pp < hw;
-      cnt += valid;
-      const float uf = (float)u, vf = (float)v;
-      o[3 * j + 0] = valid ? fmaf(d[j], fmaf(a0, uf, fmaf(b0, vf, c0)), tx) : qnan;
-      o[3 * j + 1] = valid ? fmaf(d[j], fmaf(a1, uf, fmaf(b1, vf, c1)), ty) : qnan;
-      o[3 * j + 2] = valid ? fmaf(d[j], fmaf(a2, uf, fmaf(b2, vf, c2)), tz) : qnan;
-    }
-    if (p + 3 < hw && (hw & 3) == 0) {
-      float4* o4 = reinterpret_cast<float4*>(ob + (int64_t)p * 3);
-      o4[0] = make_float4(o[0], o[1], o[2], o[3]);
-      o4[1] = make_float4(o[4], o[5], o[6], o[7]);
-      o4[2] = make_float4(o[8], o[9], o[10], o[11]);
-    } else {
-      for (int j = 0; j < 4 && p + j < hw; ++j)
-        for (int k = 0; k < 3; ++k) ob[(int64_t)(p + j) * 3 + k] = o[3 * j + k];
+    for (int k = 0; k < kCloudUnroll; ++k) {
+      const int wp = wp0 + k * 128;  // first pixel of this run
+      if (wp >= hw) break;           // (warp-uniform)
+      const int p = wp + lane * 4;
+      const float d[4] = {dq[k].x, dq[k].y, dq[k].z, dq[k].w};
+      float o[12];
+      const int v0 = p / W, u0 = p - v0 * W;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int u = u0 + j, v = v0;
+        if (!vec && u >= W) { const int pp = p + j; v = pp / W; u = pp - v * W; }
+        const bool valid = key_valid(__float_as_uint(d[j]), dmax_bits) && p + j < hw;
+        cnt += valid;
+        const float uf = (float)u, vf = (float)v;
+        o[3 * j + 0] = valid ? fmaf(d[j], fmaf(a0, uf, fmaf(b0, vf, c0)), tx) : qnan;
+        o[3 * j + 1] = valid ? fmaf(d[j], fmaf(a1, uf, fmaf(b1, vf, c1)), ty) : qnan;
+        o[3 * j + 2] = valid ? fmaf(d[j], fmaf(a2, uf, fmaf(b2, vf, c2)), tz) : qnan;
+      }
+      if (vec && wp + 128 <= hw) {
+        float4* s4 = reinterpret_cast<float4*>(st);
+        s4[3 * lane + 0] = make_float4(o[0], o[1], o[2], o[3]);
+        s4[3 * lane + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        s4[3 * lane + 2] = make_float4(o[8], o[9], o[10], o[11]);
+        __syncwarp();
+        float4* o4 = reinterpret_cast<float4*>(ob + (int64_t)wp * 3);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o4[c * 32 + lane] = s4[c * 32 + lane];
+        __syncwarp();
+      } else {
+        for (int j = 0; j < 4 && p + j < hw; ++j)
+          for (int c = 0; c < 3; ++c) ob[(int64_t)(p + j) * 3 + c] = o[3 * j + c];
+      }
     }
   }
-  if (n_valid) {
+  if (n_valid) {  // one atomic per CTA: the CTAs of a frame run together, and thousands of atomics on one word serialise
+    __shared__ int cta_cnt[8];
     cnt = warp_sum_i(cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&n_valid[f], cnt);
+    if (lane == 0) cta_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += cta_cnt[w];
+      if (t) atomicAdd(&n_valid[f], t);
+    }
   }
 }
 
@@ -3329,8 +3363,8 @@ int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, c
     if (e != cudaSuccess) return (int)e;
   }
   prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, tab);
-  const int hw4 = (H * W + 3) / 4;
-  const unsigned gx = (unsigned)std::max(1, std::min((hw4 + 255) / 256, dev->sms * 8));
+  const int hw16 = (H * W + 4 * kCloudUnroll - 1) / (4 * kCloudUnroll);  // a thread takes kCloudUnroll quads per step
+  const unsigned gx = (unsigned)std::max(1, std::min((hw16 + 255) / 256, dev->sms * 8));
   frame_cloud_kernel<<<dim3(gx, (unsigned)F), 256, 0, st>>>(depth, F, H, W, tab, dmax_to_bits(max_depth_mm), xyz,
                                                             n_valid);
   g_launches += 2;
