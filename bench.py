@@ -389,6 +389,7 @@ def run_lm3d(args):
         "peak_source": peak_src,
         "unit": "GB/s",
         "frac": achieved / peak,
+        "frac_of_nominal_8000": achieved / 8000.0,  # SURVEY 8d asks for both denominators
         "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_tma": kern[2], "lift_warp": kern[3],

@@ -93,3 +93,26 @@ def test_torch_wrappers_reject_cpu_tensors():
     with pytest.raises(ValueError, match="CUDA"):
         lift.lift_boxes(torch.zeros(1, 4, 4), torch.zeros(1, 7, dtype=torch.float64), torch.ones(1, 4, dtype=torch.float64),
                         torch.zeros(1, 4, dtype=torch.int32), torch.tensor([0, 1]))
+
+
+def test_nms_wrapper_rejects_cpu_tensors_and_bad_shapes():
+    import torch
+
+    from lm3d import nms
+
+    with pytest.raises(ValueError, match="CUDA"):
+        nms.nms_boxes(torch.zeros(3, 12), torch.zeros(3), torch.zeros(3, dtype=torch.int32))
+
+
+def test_bbox_processor_shape_without_boxes_and_no_cpu_fallback():
+    """Frames without rows come back as empty lists without touching the GPU; with rows and no CUDA device the class
+    raises (there is no CPU path behind it)."""
+    import torch
+
+    from src.mapper.bbox_optimiser import BoundingBoxProcessor
+
+    assert BoundingBoxProcessor({3: [], 7: []}, None).suppress_bboxes() == {3: [], 7: []}
+    if not torch.cuda.is_available():
+        row = [np.zeros(3), np.array([0.0, 1.0, 0.0]), np.array([1.0, 1.0, 0.0]), np.array([1.0, 0.0, 0.0]), 0, 0.9, "sign"]
+        with pytest.raises(Exception):
+            BoundingBoxProcessor({0: [row]}, None).suppress_bboxes()
