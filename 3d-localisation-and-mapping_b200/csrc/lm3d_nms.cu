@@ -268,7 +268,8 @@ __device__ __forceinline__ void warp_for_each_rival(int p, int lane, const Works
 }
 
 // 5. one relaxation round (in place), one warp per box
-__global__ void nms_round_kernel(float thr, int round, Workspace ws) {
+// (64 resident warps per SM at 32 registers beat 48 at 39, small spills included: the walk is bound by load latency)
+__global__ void __launch_bounds__(256, 8) nms_round_kernel(float thr, int round, Workspace ws) {
   if (round > 0 && ws.hdr->remaining[(round - 1) % kMaxRoundSlots] == 0) return;  // converged in an earlier round
   const int lane = threadIdx.x & 31;
   const int p = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -294,7 +295,7 @@ __global__ void nms_round_kernel(float thr, int round, Workspace ws) {
 }
 
 // 6. results in input order: keep flags and the suppressing box (the first KEPT rival in greedy order)
-__global__ void nms_finish_kernel(float thr, uint8_t* __restrict__ keep, int32_t* __restrict__ parent, Workspace ws) {
+__global__ void __launch_bounds__(256, 8) nms_finish_kernel(float thr, uint8_t* __restrict__ keep, int32_t* __restrict__ parent, Workspace ws) {
   const int lane = threadIdx.x & 31;
   const int p = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (p >= ws.hdr->cursor) return;
