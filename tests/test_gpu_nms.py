@@ -1,4 +1,6 @@
 """GPU: the CUDA 3-D NMS (lm3d_nms_boxes, through the C ABI) against the oracle: keep flags and parents bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -125,3 +127,11 @@ def test_properties_at_scale(cuda_device):
     keep2, _, _ = nms.nms_boxes(c_t[torch.from_numpy(k_idx).to(dev)].contiguous(), f_t[torch.from_numpy(k_idx).to(dev)].contiguous(),
                                 l_t[torch.from_numpy(k_idx).to(dev)].contiguous())
     assert bool(keep2.all())
+
+
+def test_committed_fixture(cuda_device):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nms_cases.npz"))
+    for name in ("clustered", "loose", "chain"):
+        keep, parent, _ = run_cuda(g[f"{name}_corners"], g[f"{name}_conf"], g[f"{name}_label"], cuda_device,
+                                   float(g[f"{name}_thr"]), float(g[f"{name}_pad"]))
+        assert np.array_equal(keep, g[f"{name}_keep"]) and np.array_equal(parent, g[f"{name}_parent"]), name

@@ -1,5 +1,7 @@
 """CPU: the 3-D NMS oracle (oracle/nms_numpy.py, NMS-SPEC v0) against known answers, an independent scalar
 restatement, and its own properties.  (Parity unpinned: the reference's bbox_optimiser.py is absent.)"""
+import os
+
 import numpy as np
 
 from nms_cases import brute_force_nms, chain_boxes, clustered_boxes
@@ -77,3 +79,14 @@ def test_suppress_rows_shape():
     assert sum(len(v) for v in out.values()) == int(keep.sum())
     kept_ids = [id(r) for v in out.values() for r in v]
     assert kept_ids == [id(rows[i]) for i in np.flatnonzero(keep)]
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "nms_cases.npz")
+
+
+def test_oracle_reproduces_the_committed_fixture():
+    g = np.load(GOLD)
+    for name in ("clustered", "loose", "chain"):
+        keep, parent = nms.nms_3d(g[f"{name}_corners"], g[f"{name}_conf"], g[f"{name}_label"], float(g[f"{name}_thr"]),
+                                  float(g[f"{name}_pad"]))
+        assert np.array_equal(keep, g[f"{name}_keep"]) and np.array_equal(parent, g[f"{name}_parent"]), name
