@@ -25,11 +25,13 @@ for a,n in agg.items():
     key=info[0] if info else None
     byline[key]+=n
     if info: byop[key][info[1].split()[0] if not info[1].startswith('@') else info[1].split()[1]]+=n
+import glob, os
+SRC_FILES = sorted(os.path.basename(f) for f in glob.glob('/root/repo/3d-localisation-and-mapping_b200/csrc/*.cu*'))
 src={}
-for f in ('lm3d_kernels.cu','lm3d_device.cuh'):
+for f in SRC_FILES:
     src[f]=open('/root/repo/3d-localisation-and-mapping_b200/csrc/'+f).read().split('\n')
 print('total',tot)
-for f in ('lm3d_kernels.cu','lm3d_device.cuh'):
+for f in SRC_FILES:
     for (ff,l),n in sorted((k,v) for k,v in byline.items() if k and k[0]==f):
         if n/tot<0.002: continue
         ops=' '.join(f"{o}:{c/slots:.1f}" for o,c in byop[(ff,l)].most_common(6))

@@ -31,8 +31,10 @@ for a,n in samp.items():
     info=addr2line.get(a-base); key=info[0] if info else None
     byline[key]+=n; byline_inst[key]+=inst[a]
     for h,c in bystall[a].items(): byline_st[key][h]+=c
+import glob, os
+SRC_FILES = sorted(os.path.basename(f) for f in glob.glob('/root/repo/3d-localisation-and-mapping_b200/csrc/*.cu*'))
 src={}
-for f in ('lm3d_kernels.cu','lm3d_device.cuh'):
+for f in SRC_FILES:
     src[f]=open('/root/repo/3d-localisation-and-mapping_b200/csrc/'+f).read().split('\n')
 print('total samples',tot)
 tots=collections.Counter()
