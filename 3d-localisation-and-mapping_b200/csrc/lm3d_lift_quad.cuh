@@ -6,11 +6,13 @@
 namespace lm3d {
 // ------------------------------------------------------------------------------------------
 // 3d. small boxes, float4 loads: one warp per box, a lane owns FOUR consecutive pixels of a row.
-//     One LDG.128 per lane and row step (16-byte aligned: the quads start at x0 & ~3), so a
-//     rect <= 64 px wide needs no column passes at all, the loads per pixel drop 4x and the
-//     bytes in flight per warp rise 4x -- the direct-load kernels above are bound by load
-//     latency (ncu: 53 % of the stall samples are long-scoreboard waits on first use).
-//     Same two-pass histogram percentile as 3b / 3c.  Needs W % 4 == 0.
+//     One 16-byte copy per lane and row step (aligned: the quads start at x0 & ~3), issued as cp.async
+//     (LDGSTS.128) two row steps ahead of its use, so a rect <= 64 px wide needs no column passes at
+//     all, the loads per pixel drop 4x and the bytes in flight per warp rise 4x -- the direct-load
+//     kernels above are bound by load latency (ncu: 53 % of the stall samples are long-scoreboard
+//     waits on first use); this one is bound by instruction issue (78 % of the slots busy).
+//     Same two-pass histogram percentile as 3b / 3c; what it cannot resolve (ties) is deferred to
+//     lift_resolve_kernel at the end of this file.  Needs W % 4 == 0.
 // ------------------------------------------------------------------------------------------
 #ifndef LM3D_QUAD_WARPS
 #define LM3D_QUAD_WARPS 8
