@@ -78,16 +78,16 @@ class ProcessPose:
         image_wh = np.empty((F, 2), dtype=np.float64)
         frame_off = np.zeros(F + 1, dtype=np.int64)
         boxes = []
-        pose_rows = self.pose.iloc if hasattr(self.pose, "iloc") else None
+        # pose row i = frame i, first column is the timestamp (pose_processor.py:109): one conversion for the whole
+        # DataFrame instead of one pandas row lookup per frame (50 us each: half a second per 10 k frames)
+        pose_np = (self.pose.iloc[:, 1:8].to_numpy(dtype=np.float64) if hasattr(self.pose, "iloc") else None)
         for i, frame_index in enumerate(frames):
             rgb_tensor, depth_tensor, ci = self.dataset[frame_index]
             _, depth_image = self.visualiser.parse_images(None, depth_tensor)
             if depth_image.shape != (H, W):
                 raise ValueError(f"frame {frame_index}: depth is {depth_image.shape}, expected {(H, W)}")
             depth[i] = depth_image
-            # pose row i = frame i, first column is the timestamp (pose_processor.py:109)
-            row = pose_rows[frame_index][1:].to_numpy() if pose_rows is not None else np.asarray(self.pose[frame_index])
-            pose7[i] = np.asarray(row, dtype=np.float64)
+            pose7[i] = pose_np[frame_index] if pose_np is not None else np.asarray(self.pose[frame_index], dtype=np.float64)
             # intrinsics rescale: every entry, cy included, by the WIDTH ratio (:133-137)
             s = ci["image_width"] / self.depth_width
             intr4[i] = (ci["fx"] / s, ci["fy"] / s, ci["cx"] / s, ci["cy"] / s)
