@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 
 #include "lm3d.h"
 #include "lm3d_device.cuh"
@@ -62,12 +63,14 @@ struct DeviceInfo {
   bool attrs_set = false;
 };
 static DeviceInfo g_dev[64];
+static std::mutex g_init_mu;  // the lazily initialised tables below (entry points are callable from several threads)
 
 static int device_info(DeviceInfo** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return LM3D_ERR_NO_DEVICE;
   if (dev < 0 || dev >= 64) return LM3D_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lock(g_init_mu);
   DeviceInfo& d = g_dev[dev];
   if (!d.ok) {
     int major = 0;
@@ -146,6 +149,7 @@ static EncodeTiledFn g_encode_tiled = nullptr;
 static bool g_encode_tried = false;
 
 static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, TileMaps* maps) {
+  std::lock_guard<std::mutex> lock(g_init_mu);
   if (!g_encode_tried) {
     g_encode_tried = true;
     cudaDriverEntryPointQueryResult q;
