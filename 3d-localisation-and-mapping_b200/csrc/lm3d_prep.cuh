@@ -36,8 +36,26 @@ __global__ void prep_frames_kernel(const double* __restrict__ pose7, const doubl
 // ------------------------------------------------------------------------------------------
 // 2. boxes: frame lookup, classification, work lists
 // ------------------------------------------------------------------------------------------
+// Largest f with off[f] <= b (b < off[F]).  Boxes are laid out frame by frame, so f is close to b * F / B: start
+// there, bracket the answer with doubling steps, bisect the bracket -- 3 loads (2 dependent) when the frames hold
+// equal numbers of boxes, instead of the log2(F) = 14 dependent loads of a plain bisection (the prep kernels are
+// nothing but this chain: 19 us for 200 k boxes).
 __device__ __forceinline__ int64_t csr_find(const int64_t* __restrict__ off, int64_t F, int64_t b) {
-  int64_t lo = 0, hi = F;  // largest f with off[f] <= b
+  const int64_t B = off[F];
+  int64_t g = (int64_t)((double)b * (double)F / (double)B);
+  g = min(max(g, (int64_t)0), F - 1);
+  int64_t lo, hi;  // invariant: off[lo] <= b < off[hi]  (off[0] = 0, off[F] = B > b)
+  if (off[g] <= b) {
+    lo = g;
+    int64_t step = 1;
+    while (lo + step < F && off[lo + step] <= b) { lo += step; step <<= 1; }
+    hi = min(F, lo + step);
+  } else {
+    hi = g;
+    int64_t step = 1;
+    while (hi - step > 0 && off[hi - step] > b) { hi -= step; step <<= 1; }
+    lo = max((int64_t)0, hi - step);
+  }
   while (hi - lo > 1) {
     const int64_t mid = (lo + hi) >> 1;
     if (off[mid] <= b) lo = mid; else hi = mid;
