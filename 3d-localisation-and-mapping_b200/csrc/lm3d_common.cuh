@@ -33,7 +33,10 @@ struct Workspace {
   int32_t* large_list;  // [B]
   int32_t* deferred;    // [B] int4 {item, key window lo, hi, -}: boxes lift_quad_kernel leaves to lift_resolve_kernel
   int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor, 4..6 rare-path stats,
-                        //       8 n_tma, 9 tma cursor, 10 n_deferred, 11 deferred cursor
+                        //       8 n_tma, 9 tma cursor, 10 n_deferred, 11 deferred cursor,
+                        //       13 tile-path boxes that needed level 2, 14 tile-path boxes handed to lift_block_kernel,
+                        //       15 tile-path collect mismatches (must stay 0), 16..19 why a box was handed over: catch-all bin,
+                        //       too few run keys / too many tiles to sample, bracket overfull, bracket missed   ([32] ints in all)
 };
 
 struct __align__(16) WorkItem {
@@ -51,7 +54,7 @@ static size_t workspace_layout(int64_t F, int64_t B, char* base, Workspace* ws) 
     off += align_up(bytes, 256);
     return p;
   };
-  char* c = take(64);
+  char* c = take(128);
   char* t = take((size_t)F * sizeof(FrameTab));
   char* bf = take((size_t)B * 4);
   char* sl = take((size_t)B * 80);

@@ -11,8 +11,10 @@
 //                            the target bins in pass 2, exact select                              (lm3d_lift_quad.cuh)
 //      lift_resolve_kernel : the boxes pass 1 / 2 could not resolve (ties), exact key-space select (lm3d_lift_quad.cuh)
 //   4. lift_block_kernel   : persistent, ONE CTA PER BOX, the same scheme at block scope          (lm3d_lift_block.cuh)
-// Alternative kernels kept for A/B runs and odd shapes: lm3d_lift_compact.cuh, lm3d_lift_tma.cuh, lm3d_lift_hist.cuh,
-// lm3d_lift_large.cuh.  The kernels live in .cuh parts that are included here, in order, into ONE translation unit
+//   5. tile pyramid        : large frames whose CTA-class boxes cover them at least once: tile_map / tile_build /
+//                            tile_box kernels per chunk of frames, before lift_block_kernel      (lm3d_lift_tiles.cuh)
+// Alternative kernels kept for A/B runs and odd shapes: lm3d_lift_tma.cuh, lm3d_lift_hist.cuh, lm3d_lift_large.cuh;
+// shared warp helpers in lm3d_warp_util.cuh.  The kernels live in .cuh parts that are included here, in order, into ONE translation unit
 // (one nvcc invocation, no relocatable device code); the host side of the C ABI follows below.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,12 +32,13 @@
 
 #include "lm3d_common.cuh"
 #include "lm3d_prep.cuh"
-#include "lm3d_lift_compact.cuh"
+#include "lm3d_warp_util.cuh"
 #include "lm3d_lift_tma.cuh"
 #include "lm3d_lift_hist.cuh"
 #include "lm3d_lift_quad.cuh"
 #include "lm3d_lift_large.cuh"
 #include "lm3d_lift_block.cuh"
+#include "lm3d_lift_tiles.cuh"
 #include "lm3d_stream.cuh"
 
 namespace lm3d {
@@ -46,11 +49,11 @@ namespace lm3d {
 std::atomic<int64_t> g_lm3d_launches{0};  // shared with lm3d_nms.cu
 static std::atomic<int64_t>& g_launches = g_lm3d_launches;
 
-// Optional per-kernel timing of lm3d_lift_boxes (bench.py's roofline leg): when enabled, six
-// events bracket the five kernels on the caller's stream.  Not thread-safe; off by default.
-constexpr int kProfKernels = 5;
+// Optional per-stage timing of lm3d_lift_boxes (bench.py's roofline leg): when enabled, seven
+// events bracket the six stages on the caller's stream.  Not thread-safe; off by default.
+constexpr int kProfKernels = 6;
 static bool g_profile = false;
-static cudaEvent_t g_prof_ev[kProfKernels + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+static cudaEvent_t g_prof_ev[kProfKernels + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 static bool g_prof_valid = false;
 static inline void prof_mark(int i, cudaStream_t st) {
   if (g_profile) cudaEventRecord(g_prof_ev[i], st);
@@ -58,7 +61,7 @@ static inline void prof_mark(int i, cudaStream_t st) {
 
 struct DeviceInfo {
   int sms = 0;
-  int small_ctas = 1, large_ctas = 1, tma_ctas = 1, hist_ctas = 1, quad_ctas = 1, blk_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
+  int large_ctas = 1, tma_ctas = 1, hist_ctas = 1, quad_ctas = 1, blk_ctas = 1, tile_ctas = 1;  // resident CTAs per SM (occupancy API) -> persistent grid size
   bool ok = false;
   bool attrs_set = false;
 };
@@ -80,14 +83,8 @@ static int device_info(DeviceInfo** out) {
     d.ok = true;
   }
   if (!d.attrs_set) {
-    e = cudaFuncSetAttribute(lift_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kSmallWarps * kSmallCap * 4);
-    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(lift_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (kLargeCap + kSortCap) * 4);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.small_ctas, lift_small_kernel, kSmallWarps * 32,
-                                                      kSmallWarps * kSmallCap * 4);
     if (e != cudaSuccess) return (int)e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.large_ctas, lift_large_kernel, kLargeThreads,
                                                       (kLargeCap + kSortCap) * 4);
@@ -114,7 +111,13 @@ static int device_info(DeviceInfo** out) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blk_ctas, lift_block_kernel, kBlkThreads, kBlkSmemWords * 4);
     if (e != cudaSuccess) return (int)e;
     d.blk_ctas = std::max(d.blk_ctas, 1);
-    d.small_ctas = std::max(d.small_ctas, 1);
+    e = cudaFuncSetAttribute(tile_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBoxSmemWords * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tile_ctas, tile_box_kernel, kBlkThreads, kTileBoxSmemWords * 4);
+    if (e != cudaSuccess) return (int)e;
+    d.tile_ctas = std::max(d.tile_ctas, 1);
+    e = cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBuildSmemWords * 4);
+    if (e != cudaSuccess) return (int)e;
     d.large_ctas = std::max(d.large_ctas, 1);
     d.attrs_set = true;
   }
@@ -130,15 +133,14 @@ static int device_info(DeviceInfo** out) {
 // floats (0: TMA path unusable for this tensor, the legacy warp kernel takes every small box).
 // Which kernel takes the warp boxes.  LM3D_WARP_PATH = "quad" (default: float4 loads, a lane owns four
 // consecutive pixels, histogram percentile; W % 4 != 0 tensors fall to "hist"), "hist" (scalar loads, a lane owns
-// a column, histogram percentile), "tma" (TMA tile ring, histogram percentile), "compact" (scalar loads, ballot
-// compaction + radix select: the round-1a kernel).  The last three are kept for A/B runs.  Read per call.
-enum WarpPath { kPathQuad = 0, kPathHist = 1, kPathTma = 2, kPathCompact = 3 };
+// a column, histogram percentile), "tma" (TMA tile ring, histogram percentile).  The last two are kept for A/B runs.
+// Read per call.
+enum WarpPath { kPathQuad = 0, kPathHist = 1, kPathTma = 2 };
 static WarpPath warp_path() {
   const char* env = getenv("LM3D_WARP_PATH");
   if (!env) return kPathQuad;
   if (!strcmp(env, "hist")) return kPathHist;
   if (!strcmp(env, "tma")) return kPathTma;
-  if (!strcmp(env, "compact")) return kPathCompact;
   return kPathQuad;
 }
 
@@ -176,6 +178,56 @@ static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, 
     span = tw;
   }
   return span;
+}
+
+// Tile-pyramid path (lm3d_lift_tiles.cuh): scratch that follows the base workspace.  The path is taken when the
+// frames are large enough to pay for a per-frame pass (H*W >= 2^18; LM3D_TILE_PATH=on forces it for any frame of at
+// least one tile, =off disables it), W % 4 == 0 and the caller's workspace holds the scratch of at least one frame.
+struct TilePlan {
+  bool on = false;
+  int ntx = 0, nty = 0, chunk = 0, n_chunks = 0;
+  uint32_t area_thr = 1;
+  size_t off_area = 0, off_cursor = 0, off_map = 0, off_sum = 0, off_cdf = 0, off_sorted = 0, bytes = 0;  // relative to the base size
+};
+static int tile_chunk_default() {
+  const char* env = getenv("LM3D_TILE_CHUNK");
+  const int v = env ? atoi(env) : 0;
+  return v > 0 ? v : 16;
+}
+static bool tile_plan(int64_t F, int32_t H, int32_t W, size_t avail, int want_chunk, TilePlan* P) {
+  *P = TilePlan();
+  const char* env = getenv("LM3D_TILE_PATH");
+  if (env && !strcmp(env, "off")) return false;
+  const bool force = env && !strcmp(env, "on");
+  if ((W & 3) != 0 || F < 1) return false;
+  if (!force && (int64_t)H * W < ((int64_t)1 << 18)) return false;
+  if (H < kTile || W < kTile) return false;
+  P->ntx = (W + kTile - 1) / kTile;
+  P->nty = (H + kTile - 1) / kTile;
+  const size_t nt = (size_t)P->ntx * P->nty;
+  const size_t per_frame = align_up(nt * sizeof(TileSum), 256) + align_up(nt * kTileBins * 2, 256) + align_up(nt * kTilePix * 4, 256);
+  int64_t chunk = std::min<int64_t>(F, want_chunk);
+  auto total = [&](int64_t c) {
+    const int64_t nc = (F + c - 1) / c;
+    return align_up((size_t)F * 4, 256) + align_up((size_t)nc * 4, 256) + align_up((size_t)c * sizeof(TileMap), 256) + (size_t)c * per_frame;
+  };
+  while (chunk >= 1 && total(chunk) > avail) chunk >>= 1;
+  if (chunk < 1) return false;
+  P->chunk = (int)chunk;
+  P->n_chunks = (int)((F + chunk - 1) / chunk);
+  size_t off = 0;
+  P->off_area = off; off += align_up((size_t)F * 4, 256);
+  P->off_cursor = off; off += align_up((size_t)P->n_chunks * 4, 256);
+  P->off_map = off; off += align_up((size_t)chunk * sizeof(TileMap), 256);
+  P->off_sum = off; off += (size_t)chunk * align_up(nt * sizeof(TileSum), 256);
+  P->off_cdf = off; off += (size_t)chunk * align_up(nt * kTileBins * 2, 256);
+  P->off_sorted = off; off += (size_t)chunk * align_up(nt * kTilePix * 4, 256);
+  P->bytes = off;
+  double cover = 1.0;
+  if (const char* c = getenv("LM3D_TILE_COVER")) cover = atof(c);
+  P->area_thr = (uint32_t)std::max(1.0, cover * (double)H * (double)W / 1024.0);
+  P->on = true;
+  return true;
 }
 
 static uint32_t dmax_to_bits(double max_depth_mm) {
@@ -233,12 +285,12 @@ int lm3d_profile_enable(int on) {
   return LM3D_OK;
 }
 
-int lm3d_profile_read(float* ms5) {
-  if (!ms5 || !g_prof_valid) return LM3D_ERR_BAD_ARG;
+int lm3d_profile_read(float* ms6) {
+  if (!ms6 || !g_prof_valid) return LM3D_ERR_BAD_ARG;
   cudaError_t e = cudaEventSynchronize(g_prof_ev[kProfKernels]);
   if (e != cudaSuccess) return (int)e;
   for (int i = 0; i < kProfKernels; ++i) {
-    e = cudaEventElapsedTime(&ms5[i], g_prof_ev[i], g_prof_ev[i + 1]);
+    e = cudaEventElapsedTime(&ms6[i], g_prof_ev[i], g_prof_ev[i + 1]);
     if (e != cudaSuccess) return (int)e;
   }
   return LM3D_OK;
@@ -247,6 +299,14 @@ int lm3d_profile_read(float* ms5) {
 size_t lm3d_workspace_bytes(int64_t F, int64_t B) {
   if (F < 0 || B < 0) return 0;
   return workspace_layout(F, B, nullptr, nullptr);
+}
+
+size_t lm3d_lift_workspace_bytes(int64_t F, int32_t H, int32_t W, int64_t B) {
+  if (F < 0 || B < 0 || H < 1 || W < 1) return 0;
+  const size_t base = workspace_layout(F, B, nullptr, nullptr);
+  TilePlan P;
+  if (!tile_plan(F, H, W, (size_t)-1, tile_chunk_default(), &P)) return base;
+  return base + P.bytes;
 }
 
 int lm3d_scale_boxes(const double* boxes_xyxy, const double* image_wh, const int64_t* frame_off, int64_t F,
@@ -275,7 +335,8 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   if ((int64_t)H * W > (int64_t)1 << 30 || B > INT32_MAX - 64 || F > INT32_MAX) return LM3D_ERR_TOO_LARGE;
   if ((((uintptr_t)depth | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)rect4) & 15) != 0)
     return LM3D_ERR_ALIGNMENT;
-  if (workspace_bytes < lm3d_workspace_bytes(F, B)) return LM3D_ERR_WORKSPACE;
+  const size_t base_bytes = lm3d_workspace_bytes(F, B);
+  if (workspace_bytes < base_bytes) return LM3D_ERR_WORKSPACE;
   DeviceInfo* dev = nullptr;
   int rc = device_info(&dev);
   if (rc != LM3D_OK) return rc;
@@ -283,8 +344,18 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws;
   workspace_layout(F, B, (char*)workspace, &ws);
-  cudaError_t e = cudaMemsetAsync(ws.counters, 0, 64, st);
+  cudaError_t e = cudaMemsetAsync(ws.counters, 0, 128, st);
   if (e != cudaSuccess) return (int)e;
+  // tile-pyramid path: uses whatever the caller's workspace holds beyond the base layout (lm3d_lift_workspace_bytes
+  // sizes it for the default chunk of frames; a smaller workspace means smaller chunks or, below one frame, no tiles)
+  TilePlan TP;
+  char* tile_base = (char*)workspace + base_bytes;
+  uint32_t* frame_area = nullptr;
+  if (tile_plan(F, H, W, workspace_bytes - base_bytes, tile_chunk_default(), &TP)) {
+    frame_area = (uint32_t*)(tile_base + TP.off_area);
+    e = cudaMemsetAsync(frame_area, 0, TP.off_map - TP.off_area, st);  // frame areas + chunk cursors
+    if (e != cudaSuccess) return (int)e;
+  }
 
   prof_mark(0, st);
   prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, ws.tab);
@@ -296,7 +367,13 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   const int tma_span = build_tile_maps(depth, F, H, W, &maps);
   prep_boxes_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, frame_off, F, B, H, W, ws.tab, ws.box_frame,
                                                                (WorkItem*)ws.small_items, (WorkItem*)ws.tma_items, tma_span,
-                                                               ws.large_list, ws.counters);
+                                                               ws.large_list, ws.counters, frame_area);
+  g_launches += 2;
+  if (TP.on) {
+    tile_route_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rect4, ws.box_frame, B, H, W, frame_area, TP.area_thr,
+                                                                 ws.large_list, ws.counters);
+    g_launches += 1;
+  }
 #ifdef LM3D_DEBUG_BOUNDS
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1002;
 #endif
@@ -324,10 +401,7 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   if (tma_span < W) {  // otherwise every warp box fits a tile class and this list is provably empty
     A.list = nullptr; A.items = ws.small_items; A.count_idx = 0; A.cursor_idx = 2;
     const int64_t want = (B + (int64_t)kSmallWarps * kSmallChunk - 1) / ((int64_t)kSmallWarps * kSmallChunk);
-    if (warp_path() == kPathCompact) {
-      const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->small_ctas));
-      lift_small_kernel<<<grid, kSmallWarps * 32, kSmallWarps * kSmallCap * 4, st>>>(A);
-    } else if (warp_path() == kPathQuad && (W & 3) == 0) {
+    if (warp_path() == kPathQuad && (W & 3) == 0) {
       const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)dev->sms * dev->quad_ctas));
       lift_quad_kernel<<<grid, kQuadWarps * 32, kQuadWarps * kQuadWarpWords * 4, st>>>(A);
       // the boxes it deferred (ties / quantised depth / bracket misses; none to a few per mille on continuous depth)
@@ -344,6 +418,34 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1003;
 #endif
   prof_mark(4, st);
+  if (TP.on) {
+    // frame chunks: bin map -> tiles -> boxes.  What a chunk's boxes cannot resolve lands on the CTA-per-box list.
+    TileArgs T;
+    T.A = A;
+    T.A.list = ws.large_list;
+    T.frame_off = frame_off; T.frame_area = frame_area; T.area_thr = TP.area_thr; T.F = F;
+    T.ntx = TP.ntx; T.nty = TP.nty;
+    T.map = (TileMap*)(tile_base + TP.off_map);
+    T.tsum = (TileSum*)(tile_base + TP.off_sum);
+    T.tcdf = (uint16_t*)(tile_base + TP.off_cdf);
+    T.tsorted = (uint32_t*)(tile_base + TP.off_sorted);
+    const int n_tiles = TP.ntx * TP.nty;
+    const unsigned box_grid = (unsigned)((int64_t)dev->sms * dev->tile_ctas);
+    for (int c = 0; c < TP.n_chunks; ++c) {
+      T.f0 = c * TP.chunk;
+      T.nf = (int)std::min<int64_t>(TP.chunk, F - T.f0);
+      T.cursor = (int32_t*)(tile_base + TP.off_cursor) + c;
+      tile_map_kernel<<<T.nf, kLargeThreads, 0, st>>>(T);
+      tile_build_kernel<<<dim3((unsigned)((n_tiles + kTileBuildWarps - 1) / kTileBuildWarps), (unsigned)T.nf), kTileBuildWarps * 32,
+                          kTileBuildSmemWords * 4, st>>>(T);
+      tile_box_kernel<<<box_grid, kBlkThreads, kTileBoxSmemWords * 4, st>>>(T);
+      g_launches += 3;
+    }
+  }
+#ifdef LM3D_DEBUG_BOUNDS
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 1006;
+#endif
+  prof_mark(5, st);
   {
     A.list = ws.large_list; A.items = nullptr; A.count_idx = 1; A.cursor_idx = 3;
     const char* lp = getenv("LM3D_LARGE_PATH");  // "legacy": the round-1a CTA kernel (also what W % 4 != 0 tensors take)
@@ -354,13 +456,13 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
       const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)dev->sms * dev->large_ctas));
       lift_large_kernel<<<grid, kLargeThreads, (kLargeCap + kSortCap) * 4, st>>>(A);
     }
+    g_launches += 1;
   }
 #ifdef LM3D_DEBUG_BOUNDS
   if (cudaStreamSynchronize(st) != cudaSuccess) return 1004;
 #endif
-  prof_mark(5, st);
+  prof_mark(6, st);
   g_prof_valid = g_profile;
-  g_launches += 3;
   return (int)cudaGetLastError();
 }
 
@@ -463,7 +565,7 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
   }
   if (frame_off[0] != 0 || frame_off[F] != B) return LM3D_ERR_BAD_ARG;
   max_boxes = std::max<int64_t>(max_boxes, 1);
-  const size_t ws_bytes = lm3d_workspace_bytes(chunk, max_boxes);
+  const size_t ws_bytes = lm3d_lift_workspace_bytes(chunk, H, W, max_boxes);
 
   // one call at a time per process on the cached buffers; a concurrent call uses private ones
   HostCache private_cache;

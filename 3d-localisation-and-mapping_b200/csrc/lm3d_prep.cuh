@@ -67,7 +67,8 @@ __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64
                                   int64_t F, int64_t B, int H, int W, const FrameTab* __restrict__ tab,
                                   int32_t* __restrict__ box_frame, WorkItem* __restrict__ small_items,
                                   WorkItem* __restrict__ tma_items, int tma_max_span,
-                                  int32_t* __restrict__ large_list, int32_t* __restrict__ counters) {
+                                  int32_t* __restrict__ large_list, int32_t* __restrict__ counters,
+                                  uint32_t* __restrict__ frame_area) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool is_small = false, is_large = false, is_tma = false;
@@ -82,6 +83,12 @@ __global__ void prep_boxes_kernel(const int32_t* __restrict__ rect4, const int64
     const int64_t area = (int64_t)(x1 - x0 + 1) * (y1 - y0 + 1);
     is_small = area <= kSmallMaxPix;
     is_large = !is_small;
+    // tile path on (section 5): a CTA-class box only adds its area to its frame's total (units of 1024 px); the
+    // frames over the cover threshold are lifted tile-wise, tile_route_kernel lists the boxes of the others
+    if (is_large && frame_area) {
+      atomicAdd(&frame_area[f], (uint32_t)((area + 1023) >> 10));
+      is_large = false;
+    }
     // TMA-fed warp kernel: the tile (16-byte aligned start column .. x1) must fit one tensor-map class
     is_tma = is_small && ((x0 & 3) + (x1 - x0 + 1) <= tma_max_span);
     is_small = is_small && !is_tma;

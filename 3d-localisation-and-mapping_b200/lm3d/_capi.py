@@ -20,6 +20,7 @@ SYMBOLS = (
     "lm3d_version",
     "lm3d_status_string",
     "lm3d_workspace_bytes",
+    "lm3d_lift_workspace_bytes",
     "lm3d_scale_boxes",
     "lm3d_lift_boxes",
     "lm3d_lift_frame_cloud",
@@ -67,6 +68,8 @@ def load():
     lib.lm3d_status_string.argtypes = [C.c_int]
     lib.lm3d_workspace_bytes.restype = sz
     lib.lm3d_workspace_bytes.argtypes = [i64, i64]
+    lib.lm3d_lift_workspace_bytes.restype = sz
+    lib.lm3d_lift_workspace_bytes.argtypes = [i64, i32, i32, i64]
     lib.lm3d_scale_boxes.restype = C.c_int
     lib.lm3d_scale_boxes.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, vp]
     lib.lm3d_lift_boxes.restype = C.c_int

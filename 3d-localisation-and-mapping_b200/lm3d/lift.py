@@ -49,8 +49,13 @@ def _stream_ptr(device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
 
 
-def workspace_bytes(F: int, B: int) -> int:
-    return int(_capi.load().lm3d_workspace_bytes(int(F), int(B)))
+def workspace_bytes(F: int, B: int, H: int | None = None, W: int | None = None) -> int:
+    """Workspace of ``lm3d_lift_boxes``: the minimum for F frames / B boxes, or -- with the frame shape -- the
+    size that also holds the tile-pyramid scratch (``lm3d_lift_workspace_bytes``)."""
+    lib = _capi.load()
+    if H is None or W is None:
+        return int(lib.lm3d_workspace_bytes(int(F), int(B)))
+    return int(lib.lm3d_lift_workspace_bytes(int(F), int(H), int(W), int(B)))
 
 
 def scale_boxes(boxes_xyxy, image_wh, frame_off, depth_w: int, depth_h: int, out=None):
@@ -78,14 +83,14 @@ def scale_boxes(boxes_xyxy, image_wh, frame_off, depth_w: int, depth_h: int, out
 class LiftPlan:
     """Pre-allocated output + workspace for repeated ``lift_boxes`` calls of one shape."""
 
-    def __init__(self, F: int, B: int, device, order_stats: bool = False):
+    def __init__(self, F: int, B: int, device, order_stats: bool = False, H: int | None = None, W: int | None = None):
         self.F, self.B = int(F), int(B)
         self.device = torch.device(device)
         self.records = torch.empty((self.B, _capi.RECORD_WORDS), dtype=torch.float32, device=self.device)
         self.order_stats = (
             torch.empty((self.B, 2), dtype=torch.float32, device=self.device) if order_stats else None
         )
-        self.ws_bytes = workspace_bytes(self.F, self.B)
+        self.ws_bytes = workspace_bytes(self.F, self.B, H, W)
         self.workspace = torch.empty((max(self.ws_bytes, 16),), dtype=torch.uint8, device=self.device)
 
 
@@ -122,7 +127,7 @@ def lift_boxes(
         if t.device != depth.device:
             raise ValueError("all tensors must live on the same device")
     if plan is None:
-        plan = LiftPlan(F, B, depth.device, order_stats)
+        plan = LiftPlan(F, B, depth.device, order_stats, H, W)
     elif plan.F < F or plan.B < B or plan.device != depth.device:
         raise ValueError("LiftPlan too small for this call")
     os_ptr = plan.order_stats.data_ptr() if plan.order_stats is not None else None

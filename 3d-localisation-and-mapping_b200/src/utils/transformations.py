@@ -38,9 +38,11 @@ class Transforms:
         return T
 
     def scale_bounding_box(self, bbox, image_size, depth_size):
-        """RGB-pixel box -> depth-pixel box, tail passed through (call site ``:174-178``)."""
+        """RGB-pixel box -> depth-pixel box, tail passed through (call site ``:174-178``).  The depth size is
+        remembered: ``bbox_to_3d`` needs it to clamp the rect the percentile depth is taken over."""
         iw, ih = image_size
         dw, dh = depth_size
+        self._depth_size = (int(dw), int(dh))
         out = list(bbox)
         out[0] = float(bbox[0]) * dw / iw
         out[1] = float(bbox[1]) * dh / ih
@@ -49,15 +51,57 @@ class Transforms:
         return out
 
     def bbox_to_3d(self, scaled_bbox, img_size=None):
-        """Four ``(x, y)`` corners TL, BL, BR, TR (call site ``:181``; order of the in-repo
-        precedent ``src/detector/detector.py:202``)."""
+        """Four ``(x, y)`` corners TL, BL, BR, TR (call site ``:181``; order of the in-repo precedent
+        ``src/detector/detector.py:202``).  The corners stay float -- the reference truncates them with ``int()``
+        itself (``:186-187``).  Also fixes the box's inclusive pixel rect (``int()`` truncation, clamped to the
+        frame) for the ``_depth_to_3d`` calls that follow: the reference comments those calls "z-values from median
+        over bbox (x, y) range" (``:183``) but passes only a corner and the depth image, so the range has to
+        travel from here (ORACLE-SPEC v0, R6 / R9)."""
         x1, y1, x2, y2 = (float(v) for v in scaled_bbox[:4])
+        size = getattr(self, "_depth_size", None)
+        if size is not None:
+            dw, dh = size
+
+            def px(v, hi):
+                return min(max(int(v), 0), hi)
+
+            xa, xb, ya, yb = px(x1, dw - 1), px(x2, dw - 1), px(y1, dh - 1), px(y2, dh - 1)
+            self._rect = (min(xa, xb), min(ya, yb), max(xa, xb), max(ya, yb))
+        else:
+            self._rect = None
+        self._rect_depth = None
         return [(x1, y1), (x1, y2), (x2, y2), (x2, y1)]
 
+    percentile = 50.0  # the reference's "median"; ProcessPose(percentile=...) of the CUDA path mirrors it
+
     def _depth_to_3d(self, x, y, depth, fx, fy, cx, cy, scale_depth):
-        """Pixel + depth -> camera-frame ``[X,Y,Z]`` (call site ``:184-196``).  ``depth`` may be
-        a scalar depth in depth units, or an ``[H,W]`` image (then the pixel's own value)."""
-        d = float(depth[int(y), int(x)]) if np.ndim(depth) == 2 else float(depth)
+        """Pixel + depth -> camera-frame ``[X,Y,Z]`` (call site ``:184-196``).
+
+        ``depth`` is the ``[H,W]`` depth image (what the reference passes) or a scalar depth in depth units.
+        With an image, z is the percentile (median) of the VALID depths (finite, > 0) inside the rect the
+        preceding ``bbox_to_3d`` fixed -- the same rule the CUDA lift and the oracle implement (R8-R10) -- and
+        the pixel is clamped to the frame (a box touching the right edge gives ``int(x) == W``).  Without a
+        preceding ``bbox_to_3d`` there is no rect and the pixel's own depth is used."""
+        if np.ndim(depth) == 2:
+            H, W = depth.shape
+            x = min(max(int(x), 0), W - 1)
+            y = min(max(int(y), 0), H - 1)
+            rect = getattr(self, "_rect", None)
+            if rect is None:
+                d = float(depth[y, x])
+            else:
+                if getattr(self, "_rect_depth", None) is None:
+                    x0, y0, x1, y1 = rect
+                    patch = np.asarray(depth[y0 : y1 + 1, x0 : x1 + 1], dtype=np.float32)
+                    with np.errstate(invalid="ignore"):
+                        ok = np.isfinite(patch) & (patch > 0)
+                    vals = patch[ok].astype(np.float64)
+                    self._rect_depth = (
+                        float(np.percentile(vals, self.percentile, method="linear")) if vals.size else float("nan")
+                    )
+                d = self._rect_depth
+        else:
+            d = float(depth)
         z = d / scale_depth
         return np.array([(x - cx) * z / fx, (y - cy) * z / fy, z], dtype=np.float64)
 

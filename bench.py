@@ -301,7 +301,7 @@ def run_lm3d(args):
     depth, pose7, intr4 = data["depth"], data["pose7"], data["intr4"]
     boxes, image_wh, frame_off = data["boxes"], data["image_wh"], data["frame_off"]
     nb = boxes.shape[0]
-    plans = [lift.LiftPlan(F, nb, dev), lift.LiftPlan(F, nb, dev)]  # double-buffered: gather(i) overlaps lift(i+1)
+    plans = [lift.LiftPlan(F, nb, dev, False, H, W), lift.LiftPlan(F, nb, dev, False, H, W)]  # double-buffered: gather(i) overlaps lift(i+1)
     plan = plans[0]
     rect4 = torch.empty((nb, 4), dtype=torch.int32, device=dev)
     gather = ldist.PipelinedGather(nb, dev) if world > 1 else None
@@ -352,8 +352,8 @@ def run_lm3d(args):
     lib.lm3d_profile_enable(1)
     import ctypes
 
-    ms4 = (ctypes.c_float * 5)()
-    kern = np.zeros(5)
+    ms4 = (ctypes.c_float * 6)()
+    kern = np.zeros(6)
     reps = max(3, min(args.steps, 10))
     for _ in range(reps):
         lift.lift_boxes(depth, pose7, intr4, rect4, frame_off, plan=plan)
@@ -363,13 +363,14 @@ def run_lm3d(args):
     kern /= reps
     # rare-path counters of the last call (workspace words 4..6): exact selects (generic fallbacks; on the quad path
     # the boxes deferred to lift_resolve_kernel), histogram passes beyond the first, candidate overflows
-    rare = [int(v) for v in plan.workspace[:64].view(torch.int32)[4:8].cpu()]
+    counters16 = [int(v) for v in plan.workspace[:128].view(torch.int32).cpu()]
+    rare = counters16[4:8]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dom = 2 + int(np.argmax(kern[2:5]))
+    dom = 2 + int(np.argmax(kern[2:6]))
     achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -381,9 +382,8 @@ def run_lm3d(args):
     roofline = {
         "bound": "hbm",
         "kernel": ["prep_frames_kernel", "prep_boxes_kernel", "lift_tma_kernel",
-                   {"compact": "lift_small_kernel", "hist": "lift_hist_kernel"}.get(os.environ.get("LM3D_WARP_PATH", ""),
-                                                                                    "lift_quad_kernel"),
-                   "lift_large_kernel"][dom],
+                   {"hist": "lift_hist_kernel"}.get(os.environ.get("LM3D_WARP_PATH", ""), "lift_quad_kernel"),
+                   "tile_map_kernel + tile_build_kernel + tile_box_kernel (all frame chunks)", "lift_block_kernel"][dom],
         "achieved": achieved,
         "peak": peak,
         "peak_source": peak_src,
@@ -393,10 +393,10 @@ def run_lm3d(args):
         "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_ms": {"prep_frames": kern[0], "prep_boxes": kern[1], "lift_tma": kern[2], "lift_warp": kern[3],
-                      "lift_large": kern[4]},
+                      "tile_path": kern[4], "lift_block": kern[5]},
         "warp_path": os.environ.get("LM3D_WARP_PATH", "quad"),
         "rare_paths": {"global_fallbacks": rare[0], "narrowing_passes": rare[1], "candidate_overflows": rare[2],
-                       "pass2_skipped": rare[3]},
+                       "pass2_skipped": rare[3], "tile_path_handed_to_block": counters16[14], "tile_level2": counters16[13], "tile_handed_why": counters16[16:20], "cta_boxes": counters16[1]},
     }
 
     # ---- e2e: HOST buffers through lm3d_lift_boxes_host --------------------------------------

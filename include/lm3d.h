@@ -58,8 +58,13 @@ typedef struct {
 int lm3d_version(void);
 const char* lm3d_status_string(int status);
 
-/* Scratch the lift needs for F frames / B boxes (frame table, box->frame map, work lists). */
+/* Scratch the lift needs for F frames / B boxes (frame table, box->frame map, work lists): the minimum
+ * lm3d_lift_boxes accepts.  lm3d_lift_workspace_bytes adds, for frames of H x W, the scratch of the tile-pyramid
+ * path (large frames whose boxes overlap heavily: per-tile summaries, histograms and bin-sorted keys for a chunk
+ * of frames); lm3d_lift_boxes uses whatever the workspace holds beyond the minimum, and falls back to one CTA per
+ * box when it holds less than one frame's worth. */
 size_t lm3d_workspace_bytes(int64_t F, int64_t B);
+size_t lm3d_lift_workspace_bytes(int64_t F, int32_t H, int32_t W, int64_t B);
 
 /* Detector boxes (RGB pixels) -> inclusive, clamped integer pixel rects at depth resolution.
  * Replaces Transforms.scale_bounding_box + bbox_to_3d + the int() truncation
@@ -83,7 +88,8 @@ int lm3d_scale_boxes(const double* boxes_xyxy, const double* image_wh, const int
  *   q_percent              percentile in [0,100] (50 = the reference's median, :183)
  *   out         [B] lm3d_box_out, 16-byte aligned
  *   order_stats [B,2] f32 or NULL: the two raw order statistics (mm) the percentile used
- *   workspace   >= lm3d_workspace_bytes(F,B) bytes, 16-byte aligned                     */
+ *   workspace   >= lm3d_workspace_bytes(F,B) bytes (lm3d_lift_workspace_bytes(F,H,W,B) enables the tile path),
+ *               16-byte aligned                                                          */
 int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
                     const double* intr4, const int32_t* rect4, const int64_t* frame_off, int64_t B,
                     double scale_depth, double max_depth_mm, double q_percent, lm3d_box_out* out,
@@ -138,13 +144,15 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
 int64_t lm3d_kernel_launches(void);
 
 /* Measurement hooks (bench.py's roofline leg; not part of the data path, not thread-safe).
- * While enabled, lm3d_lift_boxes brackets its five kernels with CUDA events on the caller's
- * stream; lm3d_profile_read waits for the last call and returns the five durations in ms:
- * [0] frame table, [1] box prep, [2] warp-per-box lift fed by TMA tiles, [3] warp-per-box
- * lift with direct loads (rects no tensor-map tile class fits, or W % 4 != 0; not launched
- * when no rect can need it), [4] CTA-per-box lift. */
+ * While enabled, lm3d_lift_boxes brackets its six stages with CUDA events on the caller's
+ * stream; lm3d_profile_read waits for the last call and returns the six durations in ms:
+ * [0] frame table (prep_frames_kernel), [1] box prep (prep_boxes_kernel, tile_route_kernel),
+ * [2] warp-per-box lift fed by TMA tiles (lift_tma_kernel; only with LM3D_WARP_PATH=tma),
+ * [3] warp-per-box lift (lift_quad_kernel + lift_resolve_kernel; lift_hist_kernel when W % 4 != 0),
+ * [4] tile-pyramid path (tile_map / tile_build / tile_box kernels of every frame chunk),
+ * [5] CTA-per-box lift (lift_block_kernel). */
 int lm3d_profile_enable(int on);
-int lm3d_profile_read(float* ms5);
+int lm3d_profile_read(float* ms6);
 
 #ifdef __cplusplus
 }

@@ -12,10 +12,10 @@ of that file cannot be satisfied in this container and are stubbed *before* impo
 * ``open3d``  (not installed): only ``o3d.camera.PinholeCameraIntrinsic`` is touched on this path
   (:144-151) and its result only feeds the dead full-frame cloud -> inert stand-in;
 * ``natsort`` (not installed): imported by ``src/detector/dataset.py`` only -> inert stand-in;
-* ``src.utils.{config,transformations,visualisation}``: ABSENT from the reference tree.  The
-  stand-in ``Transforms`` implements ORACLE-SPEC v0 through
-  ``oracle.reference_numpy``; ``Visualiser.parse_images`` passes depth through, the Open3D
-  wrappers return None.
+* ``src.utils.{config,transformations,visualisation}``: ABSENT from the reference tree.  ``Transforms`` is the
+  repo's SHIPPED restatement (``3d-localisation-and-mapping_b200/src/utils/transformations.py``, ORACLE-SPEC v0 of
+  SURVEY.md 8c, independent of ``oracle/``); ``Visualiser.parse_images`` passes depth through, the Open3D wrappers
+  return None.
 
 So the fixture pins the reference's own control flow / truncation / pose multiply / row format
 around the restated helper arithmetic -- the most that can be pinned.
@@ -30,9 +30,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 
-sys.path.insert(0, ROOT)
-from oracle import reference_numpy as ora  # noqa: E402
-
 sys.path.insert(0, os.path.join(ROOT, "3d-localisation-and-mapping_b200", "lm3d"))
 import synth  # noqa: E402  (imported as a plain module: the package dir also holds a `src` mirror)
 
@@ -46,39 +43,16 @@ def install_stubs():
     nat.natsorted = sorted
     sys.modules["natsort"] = nat
 
-    class Transforms:
-        """ORACLE-SPEC v0 stand-in for the absent src/utils/transformations.py."""
+    # The absent src/utils/transformations.py: the repo's own SHIPPED restatement (ORACLE-SPEC v0), loaded from its
+    # file so that the fixture is "the reference's ProcessPose + the helper class a user of this repo gets" -- one
+    # restatement, not a private stub.  It does not import the oracle.
+    import importlib.util
 
-        def __init__(self):
-            self._rect = None
-            self._dq = None
-
-        def get_transformation_matrix(self, pose):
-            return ora.get_transformation_matrix(pose)
-
-        def scale_bounding_box(self, bbox, image_size, depth_size):
-            self._depth_size = depth_size
-            return ora.scale_bounding_box(bbox, image_size, depth_size)
-
-        def bbox_to_3d(self, scaled_bbox, img_size):
-            dw, dh = self._depth_size
-            self._rect = ora.pixel_rect(scaled_bbox, dw, dh)
-            self._dq = None
-            x1, y1, x2, y2 = scaled_bbox[:4]
-            # float corners; the reference truncates them with int() itself (:186-187)
-            return [(x1, y1), (x1, y2), (x2, y2), (x2, y1)]
-
-        def _depth_to_3d(self, x, y, depth, fx, fy, cx, cy, scale_depth):
-            x0, y0, x1, y1 = self._rect
-            if self._dq is None:
-                patch = depth[y0 : y1 + 1, x0 : x1 + 1]
-                self._dq = ora.percentile_depth(patch[ora.valid_mask(patch)], 50.0)[0]
-            H, W = depth.shape
-            x, y = min(max(x, 0), W - 1), min(max(y, 0), H - 1)  # R6 clamp
-            return ora.depth_to_3d(x, y, self._dq, fx, fy, cx, cy, scale_depth)
-
-        def create_3d_bounding_box(self, corners, buffer):
-            return None
+    spec = importlib.util.spec_from_file_location(
+        "_shipped_transformations", os.path.join(ROOT, "3d-localisation-and-mapping_b200", "src", "utils", "transformations.py"))
+    shipped = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shipped)
+    Transforms = shipped.Transforms
 
     class Visualiser:
         def parse_images(self, rgb, depth):

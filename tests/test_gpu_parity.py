@@ -11,11 +11,11 @@ from parity import assert_records_match
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["quad", "hist", "tma", "compact"])
+@pytest.fixture(autouse=True, params=["quad", "hist", "tma"])
 def warp_kernel_path(request, monkeypatch):
     """Every parity case runs through each warp-box kernel: "quad" (default: float4 loads + histogram
-    percentile), "hist" (scalar loads + histogram percentile; also what W % 4 != 0 tensors take), "tma" (TMA tile ring + histogram percentile; rects no tile class fits and W % 4 != 0 tensors
-    still take "hist"), "compact" (ballot compaction + radix select, kept for A/B runs)."""
+    percentile), "hist" (scalar loads + histogram percentile; also what W % 4 != 0 tensors take), "tma" (TMA tile ring
+    + histogram percentile; rects no tile class fits and W % 4 != 0 tensors still take "hist")."""
     monkeypatch.setenv("LM3D_WARP_PATH", request.param)
     return request.param
 
