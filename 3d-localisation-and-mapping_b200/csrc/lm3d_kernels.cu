@@ -481,34 +481,38 @@ int lm3d_ingest_depth(const void* raw_8uc4, int64_t n_pixels, float scale, float
   return (int)cudaGetLastError();
 }
 
+size_t lm3d_cloud_workspace_bytes(int64_t F) { return F < 0 ? 0 : align_up((size_t)F * sizeof(FrameTab), 256); }
+
 int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
                           const double* intr4, double scale_depth, double max_depth_mm, float* xyz,
-                          int32_t* n_valid, void* stream) {
+                          int32_t* n_valid, void* workspace, size_t workspace_bytes, void* stream) {
   if (F < 0 || H < 1 || W < 1 || !(scale_depth > 0.0)) return LM3D_ERR_BAD_ARG;
   if (F == 0) return LM3D_OK;
-  if (!depth || !pose7 || !intr4 || !xyz) return LM3D_ERR_BAD_ARG;
-  if ((int64_t)H * W > (int64_t)1 << 30 || F > 65535) return LM3D_ERR_TOO_LARGE;
-  if ((((uintptr_t)depth | (uintptr_t)xyz) & 15) != 0) return LM3D_ERR_ALIGNMENT;
+  if (!depth || !pose7 || !intr4 || !xyz || !workspace) return LM3D_ERR_BAD_ARG;
+  if ((int64_t)H * W > (int64_t)1 << 30 || F > INT32_MAX) return LM3D_ERR_TOO_LARGE;
+  if ((((uintptr_t)depth | (uintptr_t)xyz | (uintptr_t)workspace) & 15) != 0) return LM3D_ERR_ALIGNMENT;
+  if (workspace_bytes < lm3d_cloud_workspace_bytes(F)) return LM3D_ERR_WORKSPACE;
   DeviceInfo* dev = nullptr;
   int rc = device_info(&dev);
   if (rc != LM3D_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  FrameTab* tab = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&tab, (size_t)F * sizeof(FrameTab), st);
-  if (e != cudaSuccess) return (int)e;
+  FrameTab* tab = (FrameTab*)workspace;  // the frame table lives in the caller's workspace: nothing is allocated here
   if (n_valid) {
-    e = cudaMemsetAsync(n_valid, 0, (size_t)F * 4, st);
+    cudaError_t e = cudaMemsetAsync(n_valid, 0, (size_t)F * 4, st);
     if (e != cudaSuccess) return (int)e;
   }
   prep_frames_kernel<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(pose7, intr4, F, 1.0 / scale_depth, tab);
   const int hw16 = (H * W + 4 * kCloudUnroll - 1) / (4 * kCloudUnroll);  // a thread takes kCloudUnroll quads per step
   const unsigned gx = (unsigned)std::max(1, std::min((hw16 + 255) / 256, dev->sms * 8));
-  frame_cloud_kernel<<<dim3(gx, (unsigned)F), 256, 0, st>>>(depth, F, H, W, tab, dmax_to_bits(max_depth_mm), xyz,
-                                                            n_valid);
-  g_launches += 2;
-  e = cudaGetLastError();
-  cudaFreeAsync(tab, st);
-  return (int)e;
+  const size_t hw = (size_t)H * W;
+  for (int64_t f0 = 0; f0 < F; f0 += 65535) {  // grid.y carries the frame: 65535 frames per launch
+    const int64_t nf = std::min<int64_t>(65535, F - f0);
+    frame_cloud_kernel<<<dim3(gx, (unsigned)nf), 256, 0, st>>>(depth + f0 * hw, nf, H, W, tab + f0, dmax_to_bits(max_depth_mm),
+                                                              xyz + f0 * hw * 3, n_valid ? n_valid + f0 : nullptr);
+    g_launches += 1;
+  }
+  g_launches += 1;
+  return (int)cudaGetLastError();
 }
 
 // Staging buffers of the host entry point, kept per device between calls (a sequence is usually lifted many
@@ -531,7 +535,7 @@ struct HostCache {
   bool in_use = false;
 };
 HostCache g_host_cache[64];
-std::atomic_flag g_host_lock = ATOMIC_FLAG_INIT;
+std::atomic<int> g_host_lock[64];  // one flag per device: calls on different GPUs of one process do not contend
 
 void host_slot_free(HostSlot& S) {
   cudaFree(S.depth); cudaFree(S.pose); cudaFree(S.intr); cudaFree(S.wh); cudaFree(S.off);
@@ -551,6 +555,16 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
   if (B == 0) return LM3D_OK;
   if (F < 1 || !depth || !pose7 || !intr4 || !boxes_xyxy || !image_wh || !frame_off || !out) return LM3D_ERR_BAD_ARG;
   if (device < 0 || device >= 64) return LM3D_ERR_NO_DEVICE;
+  // the CSR offsets index the caller's arrays below: check them before anything reads through them
+  if (frame_off[0] != 0 || frame_off[F] != B) return LM3D_ERR_BAD_ARG;
+  for (int64_t f = 0; f < F; ++f)
+    if (frame_off[f + 1] < frame_off[f]) return LM3D_ERR_BAD_ARG;
+  // run on `device`, and leave the caller's current device as it was on every exit path
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  if (cudaGetDevice(&guard.prev) != cudaSuccess) guard.prev = -1;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return LM3D_ERR_NO_DEVICE;
 
@@ -563,13 +577,12 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
     const int64_t f1 = std::min(F, f0 + chunk);
     max_boxes = std::max(max_boxes, frame_off[f1] - frame_off[f0]);
   }
-  if (frame_off[0] != 0 || frame_off[F] != B) return LM3D_ERR_BAD_ARG;
   max_boxes = std::max<int64_t>(max_boxes, 1);
   const size_t ws_bytes = lm3d_lift_workspace_bytes(chunk, H, W, max_boxes);
 
   // one call at a time per process on the cached buffers; a concurrent call uses private ones
   HostCache private_cache;
-  bool cached = !g_host_lock.test_and_set(std::memory_order_acquire);
+  bool cached = g_host_lock[device].exchange(1, std::memory_order_acquire) == 0;
   HostCache& C = cached ? g_host_cache[device] : private_cache;
   int rc = LM3D_OK;
   auto ck = [&](cudaError_t err) { if (err != cudaSuccess && rc == LM3D_OK) rc = (int)err; return err == cudaSuccess; };
@@ -621,7 +634,7 @@ int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, co
       for (int s = 0; s < 2; ++s) host_slot_free(C.slot[s]);
       C = HostCache();
     }
-    g_host_lock.clear(std::memory_order_release);
+    g_host_lock[device].store(0, std::memory_order_release);
   } else {
     for (int s = 0; s < 2; ++s) host_slot_free(private_cache.slot[s]);
   }

@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
 #if LM3D_QUAD_BREAK
                 if (st + i >= nsteps) break;
 #endif
-                cp_async_wait<kQuadDepth - 1>();
+                cp_async_wait<kQuadDepth2 - 1>();
                 const uint4 q0 = lds_u4(pipe_s + i * 512);
                 cp_async_16(pipe_s + i * 512, gp, (nxt_row < rows_l) ? 16u : 0u);
                 cp_async_commit();

@@ -23,6 +23,7 @@ SYMBOLS = (
     "lm3d_lift_workspace_bytes",
     "lm3d_scale_boxes",
     "lm3d_lift_boxes",
+    "lm3d_cloud_workspace_bytes",
     "lm3d_lift_frame_cloud",
     "lm3d_ingest_depth",
     "lm3d_lift_boxes_host",
@@ -75,7 +76,9 @@ def load():
     lib.lm3d_lift_boxes.restype = C.c_int
     lib.lm3d_lift_boxes.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp, sz, vp]
     lib.lm3d_lift_frame_cloud.restype = C.c_int
-    lib.lm3d_lift_frame_cloud.argtypes = [vp, i64, i32, i32, vp, vp, dbl, dbl, vp, vp, vp]
+    lib.lm3d_lift_frame_cloud.argtypes = [vp, i64, i32, i32, vp, vp, dbl, dbl, vp, vp, vp, sz, vp]
+    lib.lm3d_cloud_workspace_bytes.restype = sz
+    lib.lm3d_cloud_workspace_bytes.argtypes = [i64]
     lib.lm3d_ingest_depth.restype = C.c_int
     lib.lm3d_ingest_depth.argtypes = [vp, i64, C.c_float, vp, vp]
     lib.lm3d_lift_boxes_host.restype = C.c_int

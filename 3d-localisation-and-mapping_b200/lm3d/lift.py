@@ -158,12 +158,17 @@ def lift_frame_cloud(depth, pose7, intr4, scale_depth: float = 1000.0, max_depth
     F, H, W = depth.shape
     _chk(pose7, "pose7", torch.float64, 2)
     _chk(intr4, "intr4", torch.float64, 2)
+    if pose7.shape != (F, 7) or intr4.shape != (F, 4):
+        raise ValueError("shape mismatch: pose7 [F,7], intr4 [F,4]")
+    if pose7.device != depth.device or intr4.device != depth.device:
+        raise ValueError("all tensors must live on the same device")
     xyz = torch.empty((F, H, W, 3), dtype=torch.float32, device=depth.device)
     n_valid = torch.empty((F,), dtype=torch.int32, device=depth.device)
+    ws = torch.empty((max(int(lib.lm3d_cloud_workspace_bytes(F)), 16),), dtype=torch.uint8, device=depth.device)
     with torch.cuda.device(depth.device):
         st = lib.lm3d_lift_frame_cloud(
             depth.data_ptr(), F, H, W, pose7.data_ptr(), intr4.data_ptr(), float(scale_depth), float(max_depth_mm),
-            xyz.data_ptr(), n_valid.data_ptr(), _stream_ptr(depth.device),
+            xyz.data_ptr(), n_valid.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(depth.device),
         )
     _capi.check(st, "lm3d_lift_frame_cloud")
     return xyz, n_valid

@@ -115,6 +115,17 @@ class ArrayDataset:
     def __getitem__(self, idx):
         return None, self.depth[idx], self.intrinsics[idx]
 
+    def batch(self, frames, depth_out):
+        """Batched form used by the drop-in ``ProcessPose``: depth of ``frames`` into ``depth_out [n,H,W]``,
+        returns ``[n,6]`` = fx, fy, cx, cy, image_width, image_height (RGB resolution)."""
+        idx = np.asarray(frames, dtype=np.int64)
+        np.take(self.depth, idx, axis=0, out=depth_out)
+        cal = np.empty((len(idx), 6), dtype=np.float64)
+        for i, f in enumerate(idx):
+            ci = self.intrinsics[int(f)]
+            cal[i] = (ci["fx"], ci["fy"], ci["cx"], ci["cy"], ci["image_width"], ci["image_height"])
+        return cal
+
 
 def _quat_mul(a, b):
     ax, ay, az, aw = a

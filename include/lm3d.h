@@ -98,10 +98,12 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
 /* Full-frame world point cloud: replaces Visualiser.gen_rgbd + gen_point_cloud
  * (pose_processor.py:154-156, 262-271; Open3D unprojection + extrinsic) for F frames.
  *   xyz [F,H,W,3] f32 world coordinates, NaN where the depth pixel is invalid
- *   n_valid [F] i32 (may be NULL)                                                        */
+ *   n_valid [F] i32 (may be NULL)
+ *   workspace >= lm3d_cloud_workspace_bytes(F) bytes, 16-byte aligned (the frame table)      */
+size_t lm3d_cloud_workspace_bytes(int64_t F);
 int lm3d_lift_frame_cloud(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
                           const double* intr4, double scale_depth, double max_depth_mm, float* xyz,
-                          int32_t* n_valid, void* stream);
+                          int32_t* n_valid, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Depth ingest: replaces the byte reinterpretation + metres -> millimetres scaling of
  * ImageDataset._load_depth_image (src/detector/dataset.py:70-77) for a whole batch of decoded depth PNGs.
@@ -134,7 +136,9 @@ int lm3d_nms_boxes(const float* corners, int64_t stride_floats, const float* con
  * sequence to the device in frame chunks on two streams (copy overlapped with compute), runs
  * lm3d_scale_boxes + lm3d_lift_boxes, copies the records back, synchronises.  All pointers are
  * HOST pointers (pinned memory makes the copies asynchronous).  boxes_xyxy are RGB-pixel
- * detector boxes; intr4 is at depth resolution.  device = CUDA ordinal.                  */
+ * detector boxes; intr4 is at depth resolution.  device = CUDA ordinal (the caller's current
+ * device is restored before returning).  frame_off is validated first: frame_off[0] == 0,
+ * non-decreasing, frame_off[F] == B, else LM3D_ERR_BAD_ARG.                              */
 int lm3d_lift_boxes_host(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
                          const double* intr4, const double* boxes_xyxy, const double* image_wh,
                          const int64_t* frame_off, int64_t B, double scale_depth, double max_depth_mm,

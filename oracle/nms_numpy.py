@@ -16,7 +16,8 @@ NMS-SPEC v0 (every rule DEFINED here, fp32 arithmetic, one rounding per operatio
 * N1  extent of a box = axis-aligned bounds of its four world corners, grown by ``pad`` metres on every side
       (a sign seen head-on has no thickness along its normal; ``pad`` = the reference's ``bbox_depth_buffer``,
       ``pose_processor.py:50``, default 0.03): ``lo = min_c(corner) - pad``, ``hi = max_c(corner) + pad``.
-* N2  a box takes part iff its 12 corner coordinates are finite (lift records with ``n_valid == 0`` are NaN).
+* N2  a box takes part iff its 12 corner coordinates AND its confidence are finite (lift records with
+      ``n_valid == 0`` are NaN; a NaN confidence has no place in the greedy order).
 * N3  volume ``vol = ((hi.x - lo.x) * (hi.y - lo.y)) * (hi.z - lo.z)``.
 * N4  for two boxes ``d_k = min(hi_a.k, hi_b.k) - max(lo_a.k, lo_b.k)``; they overlap iff every ``d_k > 0`` and
       ``inter = (d.x * d.y) * d.z``, ``union = (vol_a + vol_b) - inter``, ``inter > thr * union``.
@@ -58,11 +59,12 @@ def nms_3d(corners, conf, label, thr: float = 0.1, pad: float = 0.03):
     """N6/N7, the plain sequential greedy loop (O(B * kept))."""
     lo, hi, vol, valid = box_extents(corners, pad)
     conf = np.asarray(conf, dtype=F32)
+    valid = valid & np.isfinite(conf)  # N2
     label = np.asarray(label, dtype=np.int32)
     B = lo.shape[0]
     keep = np.zeros(B, dtype=np.uint8)
     parent = np.full(B, -1, dtype=np.int32)
-    order = np.lexsort((np.arange(B), -conf.astype(np.float64)))  # conf descending, index ascending
+    order = np.lexsort((np.arange(B), -np.where(valid, conf, 0).astype(np.float64)))  # conf descending, index ascending
     kept: list[int] = []
     for i in order:
         if not valid[i]:

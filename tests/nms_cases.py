@@ -42,12 +42,12 @@ def brute_force_nms(corners, conf, label, thr, pad):
     lo = np.zeros((B, 3), f); hi = np.zeros((B, 3), f); vol = np.zeros(B, f); ok = np.zeros(B, bool)
     for i in range(B):
         c = corners[i].reshape(4, 3)
-        ok[i] = bool(np.isfinite(c).all())
+        ok[i] = bool(np.isfinite(c).all()) and bool(np.isfinite(conf[i]))  # N2
         for k in range(3):
             lo[i, k] = f(min(c[:, k])) - f(pad)
             hi[i, k] = f(max(c[:, k])) + f(pad)
         vol[i] = f(f((hi[i, 0] - lo[i, 0]) * (hi[i, 1] - lo[i, 1])) * (hi[i, 2] - lo[i, 2]))
-    order = sorted(range(B), key=lambda i: (-float(conf[i]), i))
+    order = sorted((i for i in range(B) if ok[i]), key=lambda i: (-float(conf[i]), i))
     keep = np.zeros(B, np.uint8); parent = np.full(B, -1, np.int32); kept = []
     for i in order:
         if not ok[i]:

@@ -51,6 +51,52 @@ def test_process_pose_order_empty_and_ragged_frames(cuda_device):
             assert_close_coords(np.stack(out[f][b][:4]), np.stack(want[f][b][:4]), f"frame {f} box {b}")
 
 
+def test_columnar_records_equal_rows_and_chunked_gather(cuda_device, tmp_path, monkeypatch):
+    """get_global_records() == get_global_coordinates() (same corners, same order), survives save / load, and a
+    gather in small frame chunks (bounded host memory) gives byte-identical records."""
+    from lm3d import synth
+    from src.mapper import pose_processor as ppm
+
+    seq = synth.make_sequence(9, 256, 192, 5, seed=31)
+    full = seq.bbox_coordinates()
+    bc = {k: full[k] for k in (4, 0, 7, 2, 8, 1)}
+    bc[7] = []
+    pp = ppm.ProcessPose(seq.pose_dataframe(), seq.dataset(), bc, 640, 192, 256)
+    lr = pp.get_global_records()
+    rows = pp.get_global_coordinates()
+    assert lr.frames.tolist() == [4, 0, 7, 2, 8, 1] and lr.frame_off.tolist() == [0, 5, 10, 10, 15, 20, 25]
+    lr.save(tmp_path / "r.npz")
+    back = ppm.LiftedRecords.load(tmp_path / "r.npz").to_rows()
+    assert list(back.keys()) == list(rows.keys())
+    for f in rows:
+        assert len(rows[f]) == len(back[f])
+        for ra, rb in zip(rows[f], back[f]):
+            assert all(np.array_equal(x, y) for x, y in zip(ra[:4], rb[:4])) and ra[4:] == rb[4:]
+    monkeypatch.setattr(ppm, "GATHER_CHUNK_BYTES", 2 * 256 * 192 * 4)   # two frames per chunk
+    lr2 = ppm.ProcessPose(seq.pose_dataframe(), seq.dataset(), bc, 640, 192, 256).get_global_records()
+    assert lr2.records.tobytes() == lr.records.tobytes()
+    # frame by frame through the reference's dataset[i] interface: the same bytes again
+    class Plain:
+        def __getitem__(self, i):
+            return None, seq.depth[i], seq.intrinsics[i]
+
+    lr3 = ppm.ProcessPose(seq.pose_dataframe(), Plain(), bc, 640, 192, 256).get_global_records()
+    assert lr3.records.tobytes() == lr.records.tobytes()
+
+
+def test_host_entry_rejects_bad_csr_and_restores_the_device(cuda_device):
+    from lm3d import _capi, lift, synth
+
+    seq = synth.make_sequence(3, 256, 192, 2, seed=1)
+    args = (seq.depth, seq.pose7, seq.intr4_depth_res(), seq.boxes.reshape(-1, 4), seq.image_wh())
+    for bad in ([0, 4, 2, 6], [1, 2, 4, 6], [0, 2, 4, 5]):   # non-monotone, off[0] != 0, off[F] != B
+        with pytest.raises(_capi.Lm3dError):
+            lift.lift_boxes_host(*args, np.array(bad, dtype=np.int64))
+    before = torch.cuda.current_device()
+    lift.lift_boxes_host(*args, seq.frame_off(), device=0)
+    assert torch.cuda.current_device() == before
+
+
 def test_frame_cloud_matches_oracle(cuda_device):
     from lm3d import lift, synth
 

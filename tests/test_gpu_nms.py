@@ -52,11 +52,12 @@ def test_ties_invalid_and_duplicates(cuda_device):
     conf[:] = np.round(conf, 1)                     # heavy confidence ties: index order decides
     corners[::7] = np.nan                           # lift records with n_valid == 0
     corners[3] = corners[10]; label[3] = label[10]  # exact duplicates
-    conf[20] = np.nan
+    conf[20] = np.nan                               # N2: a non-finite confidence takes a box out, like a NaN corner
+    conf[21] = np.inf
     keep, parent, _ = run_cuda(corners, conf, label, cuda_device)
-    want_keep, want_parent = ora.nms_3d(np.where(np.isnan(conf)[:, None, None], np.nan, corners), conf, label)
+    want_keep, want_parent = ora.nms_3d(corners, conf, label)
     assert np.array_equal(keep, want_keep) and np.array_equal(parent, want_parent)
-    assert (parent[::7] == -1).all() and parent[20] == -1
+    assert (parent[::7] == -1).all() and parent[20] == -1 and parent[21] == -1
 
 
 def test_empty_and_all_invalid(cuda_device):

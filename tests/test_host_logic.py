@@ -66,6 +66,56 @@ def test_process_pose_batches_like_the_reference_loop():
     np.testing.assert_array_equal(boxes[3], seq.boxes[3, 0])
 
 
+def test_process_pose_gather_frame_by_frame_equals_batched():
+    """A dataset without ``batch`` is read with ``dataset[i]`` like the reference; the result is the same."""
+    from lm3d import synth
+    from src.mapper.pose_processor import ProcessPose
+
+    seq = synth.make_sequence(5, 32, 24, 2, seed=10)
+    bc = seq.bbox_coordinates()
+
+    class PlainDataset:  # the reference's ImageDataset interface only
+        def __getitem__(self, i):
+            return None, seq.depth[i], seq.intrinsics[i]
+
+    a = ProcessPose(seq.pose_dataframe(), seq.dataset(), bc, 640, 24, 32)._gather()
+    b = ProcessPose(seq.pose_dataframe(), PlainDataset(), bc, 640, 24, 32)._gather()
+    assert a[0] == b[0]
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
+def test_lifted_records_round_trip_and_rows(tmp_path):
+    """The columnar wire format: save -> load is lossless without pickle; to_rows() gives the
+    reference's nested-list form (pose_processor.py:208) with (3,) float64 corners."""
+    import pickle
+
+    from lm3d import lift
+    from src.mapper.pose_processor import LiftedRecords
+
+    rng = np.random.default_rng(1)
+    B = 7
+    rec = np.zeros(B, dtype=lift.RECORD_DTYPE)
+    rec["corners"] = rng.normal(size=(B, 4, 3)).astype(np.float32)
+    rec["n_valid"] = np.arange(B)
+    rec["centroid"][2] = np.nan
+    lr = LiftedRecords(rec, np.array([0, 3, 3, 7], dtype=np.int64), np.array([5, 2, 9]), np.arange(B) % 2,
+                       rng.random(B), np.array(["stop", "yield", "stop", "a", "b", "c", "d"]))
+    path = tmp_path / "lifted.npz"
+    lr.save(path)
+    back = LiftedRecords.load(path)
+    assert back.records.tobytes() == rec.tobytes() and back.records.dtype == lift.RECORD_DTYPE
+    assert back.frame_off.tolist() == [0, 3, 3, 7] and back.frames.tolist() == [5, 2, 9]
+    assert back.label.tolist() == lr.label.tolist() and np.array_equal(back.conf, lr.conf)
+    rows = back.to_rows()
+    assert list(rows.keys()) == [5, 2, 9] and [len(v) for v in rows.values()] == [3, 0, 4]
+    r = rows[9][1]   # box 4
+    assert len(r) == 7 and all(isinstance(c, np.ndarray) and c.shape == (3,) and c.dtype == np.float64 for c in r[:4])
+    np.testing.assert_array_equal(np.stack(r[:4]), rec["corners"][4].astype(np.float64))
+    assert r[4:] == [0, float(lr.conf[4]), "b"]
+    pickle.loads(pickle.dumps(rows))
+
+
 def test_shard_ranges_cover_all_frames():
     from lm3d import dist as ldist
 

@@ -84,3 +84,76 @@ def test_gpu_ingest_then_lift_matches_oracle(cuda_device):
     torch.cuda.synchronize()
     want = ora.lift_boxes(want_mm, pose7, intr4, rect4, frame_off)
     assert_records_match(lift.records_to_numpy(rec), os_.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------------------------------
+# batched loader (SURVEY 8f row 2 as written): PNG + YAML files -> [F,H,W] on the device
+# ---------------------------------------------------------------------------------------
+def _write_scan(tmp_path, raw, yaml_text, names=None):
+    """Files as the reference's extraction step leaves them (detector/database_query.py:28-42): N.png depth in 8UC4,
+    N.yaml calibration, N.jpg colour (empty here: the lift never reads it)."""
+    import cv2
+
+    for d in ("rgb", "depth", "calib"):
+        (tmp_path / d).mkdir()
+    names = names or [str(i + 1) for i in range(len(raw))]
+    for n, img in zip(names, raw):
+        assert cv2.imwrite(str(tmp_path / "depth" / f"{n}.png"), img)
+        (tmp_path / "rgb" / f"{n}.jpg").write_bytes(b"")
+        (tmp_path / "calib" / f"{n}.yaml").write_text(yaml_text)
+    return str(tmp_path / "depth"), str(tmp_path / "calib"), str(tmp_path / "rgb")
+
+
+def test_depth_sequence_pairs_files_in_natural_order_and_parses_calibration(tmp_path):
+    from lm3d import ingest
+
+    g = np.load(GOLD)
+    raw = g["raw_8uc4"]
+    names = ["10", "2", "1"]   # natural order: 1, 2, 10 (dataset.py:32-33 uses natsorted)
+    depth_dir, calib_dir, rgb_dir = _write_scan(tmp_path, raw, str(g["yaml_text"]), names)
+    (tmp_path / "depth" / "99.png").write_bytes(b"x")   # a depth file without its jpg is not a frame (dataset.py:39-49)
+    seq = ingest.DepthSequence.from_dirs(depth_dir, calib_dir, image_dir=rgb_dir, depth_width=48, depth_height=64)
+    assert len(seq) == 3 and [os.path.basename(p) for p in seq.depth_paths] == ["1.png", "2.png", "10.png"]
+    cal = seq.calibration([0, 2])
+    _, _, calib = _gold()
+    assert cal.shape == (2, 6)
+    assert cal[0].tolist() == [calib["fx"], calib["fy"], calib["cx"], calib["cy"], calib["image_width"], calib["image_height"]]
+    import torch
+
+    if not torch.cuda.is_available():   # no CPU conversion path behind the loader
+        with pytest.raises(Exception):
+            seq.batch_device([0, 1])
+
+
+@pytest.mark.gpu
+def test_depth_sequence_matches_reference_loader_and_feeds_process_pose(cuda_device, tmp_path):
+    """PNG / YAML files -> DepthSequence.batch_device == the reference's own _load_depth_image output (fixture), for
+    any frame order and slot size; ProcessPose fed by the loader == ProcessPose fed by the decoded arrays."""
+    import torch
+    from lm3d import ingest, synth
+    from src.mapper.pose_processor import ProcessPose
+
+    g = np.load(GOLD)
+    raw, want = g["raw_8uc4"], g["depth_mm"]
+    F, H, W = want.shape
+    depth_dir, calib_dir, rgb_dir = _write_scan(tmp_path, raw, str(g["yaml_text"]))
+    for slot in (1, 2, 256):
+        seq = ingest.DepthSequence.from_dirs(depth_dir, calib_dir, image_dir=rgb_dir, depth_width=W, depth_height=H,
+                                             slot_frames=slot, workers=3)
+        order = [2, 0, 1, 0]
+        got, cal = seq.batch_device(order)
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+        nan = np.isnan(want[order])
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got.view(np.uint32)[~nan], want[order].view(np.uint32)[~nan])
+        assert cal.shape == (4, 6) and cal[0, 4] == 1440.0
+    # the drop-in on top of it
+    rng = np.random.default_rng(5)
+    pose = synth.Sequence(depth=want, pose7=synth.make_poses(F, rng), intrinsics=[], boxes=np.zeros((F, 1, 4)),
+                          damage_cls=None, conf=None, label=None, depth_width=W, depth_height=H).pose_dataframe()
+    bc = {0: [[100.0, 200.0, 900.0, 1500.0, 0, 0.9, "stop"], [0.0, 0.0, 1440.0, 1920.0, 1, 0.8, "yield"]], 2: [], 1: [[30.0, 40.0, 700.0, 800.0, 0, 0.7, "stop"]]}
+    _, _, calib = _gold()
+    a = ProcessPose(pose, seq, bc, 640, W, H).get_global_records()
+    b = ProcessPose(pose, synth.ArrayDataset(want, [calib] * F), bc, 640, W, H).get_global_records()
+    assert a.records.tobytes() == b.records.tobytes() and a.label.tolist() == ["stop", "yield", "stop"]

@@ -99,3 +99,23 @@ def test_full_frame_cloud_matches_per_box_lift():
     rec = ora.lift_box(depth, (0, 0, 4, 5), T, 3.0, 3.5, 2.0, 2.5)
     np.testing.assert_allclose(pts.mean(0), rec["centroid"], rtol=1e-12)
     np.testing.assert_allclose(pts.min(0), rec["aabb_min"], rtol=1e-12)
+
+
+def test_rotation_rule_r3_against_scipy():
+    """R3 (quaternion -> rotation, scalar LAST as in RTAB-Map's pose file, src/mapper/database_query.py:22) checked
+    against an independent implementation: scipy.spatial.transform.Rotation.from_quat is scalar-last too."""
+    Rotation = pytest.importorskip("scipy.spatial.transform").Rotation
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        q = rng.normal(size=4) * rng.uniform(0.1, 10.0)        # un-normalised on purpose: R3 normalises first
+        t = rng.normal(size=3)
+        T = ora.get_transformation_matrix([*t, *q])
+        np.testing.assert_allclose(T[:3, :3], Rotation.from_quat(q).as_matrix(), atol=1e-14)
+        np.testing.assert_allclose(T[:3, 3], t)
+        p = rng.normal(size=3)
+        np.testing.assert_allclose(ora.transform_to_global(p, [*t, *q]), Rotation.from_quat(q).apply(p) + t, atol=1e-13)
+    # and the shipped Transforms (the class the reference's ProcessPose calls) is the same rule
+    from src.utils.transformations import Transforms
+
+    q = np.array([0.1, -0.7, 0.3, 0.64])
+    np.testing.assert_allclose(Transforms().get_rotation([0, 0, 0, *q]), Rotation.from_quat(q).as_matrix(), atol=1e-14)

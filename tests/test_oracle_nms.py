@@ -36,6 +36,16 @@ def test_invalid_boxes_do_not_take_part():
     assert keep.tolist() == [0, 1, 0] and parent.tolist() == [-1, 1, 1]
 
 
+def test_non_finite_confidence_does_not_take_part():
+    """N2 covers the confidence too (the CUDA kernel, the header and the oracle agree): NaN / inf confidences neither
+    suppress nor get suppressed."""
+    c = np.stack([square(0), square(0), square(0), square(0)])
+    keep, parent = nms.nms_3d(c, [np.nan, 0.5, np.inf, 0.4], [0, 0, 0, 0])
+    assert keep.tolist() == [0, 1, 0, 0] and parent.tolist() == [-1, 1, -1, 1]
+    want = brute_force_nms(c, np.array([np.nan, 0.5, np.inf, 0.4], np.float32), np.zeros(4, np.int32), 0.1, 0.03)
+    assert np.array_equal(keep, want[0]) and np.array_equal(parent, want[1])
+
+
 def test_iou_threshold_and_padding():
     # two unit squares shifted by 0.5 along x, pad 0.5: extents 2 x 2 x 1, inter 1.5 x 2 x 1 = 3, union 5 -> IoU 0.6
     c = np.stack([square(0), square(0.5)])

@@ -16,9 +16,10 @@ for F, H, W in ((2000, 256, 192), (40, 1920, 1440)):
     depth, pose7, intr4 = data["depth"], data["pose7"], data["intr4"]
     xyz = torch.empty((F, H, W, 3), dtype=torch.float32, device=dev)
     nv = torch.empty((F,), dtype=torch.int32, device=dev)
+    ws = torch.empty((int(lib.lm3d_cloud_workspace_bytes(F)),), dtype=torch.uint8, device=dev)
     def call():
         _capi.check(lib.lm3d_lift_frame_cloud(depth.data_ptr(), F, H, W, pose7.data_ptr(), intr4.data_ptr(), 1000.0, float("inf"),
-                                              xyz.data_ptr(), nv.data_ptr(), _stream_ptr(dev)), "lm3d_lift_frame_cloud")
+                                              xyz.data_ptr(), nv.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "lm3d_lift_frame_cloud")
     for _ in range(10):
         call()
     reps = 40
