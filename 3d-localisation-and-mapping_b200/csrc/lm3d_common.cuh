@@ -34,9 +34,8 @@ struct Workspace {
   int32_t* deferred;    // [B] int4 {item, key window lo, hi, -}: boxes lift_quad_kernel leaves to lift_resolve_kernel
   int32_t* counters;    // [16]: 0 n_small, 1 n_large, 2 small cursor, 3 large cursor, 4..6 rare-path stats,
                         //       8 n_tma, 9 tma cursor, 10 n_deferred, 11 deferred cursor,
-                        //       13 tile-path boxes that needed level 2, 14 tile-path boxes handed to lift_block_kernel,
-                        //       15 tile-path collect mismatches (must stay 0), 16..19 why a box was handed over: catch-all bin,
-                        //       too few run keys / too many tiles to sample, bracket overfull, bracket missed   ([32] ints in all)
+                        //       14 tile-path boxes handed to lift_block_kernel, 15 tile-path collect mismatches (must stay 0)
+                        //       ([32] ints in all)
 };
 
 struct __align__(16) WorkItem {
@@ -106,7 +105,27 @@ struct LiftArgs {
   double scale_depth;
   lm3d_box_out* out;
   float* order_stats;
+  // fused record gather (multi-GPU): every finished record is also stored into the gather buffers of n_peer devices
+  // (peer-mapped memory over NVLink; this device's own buffer is one of them), at record index peer_off + b
+  lm3d_box_out* peer[8];
+  long long peer_off;
+  int n_peer;
 };
+
+// Called by the thread that has just written record b: re-read it (own stores are visible to the thread) and push it
+// to the peers.  Kernel completion makes the peer stores visible to their devices; nothing else synchronises.
+__device__ __forceinline__ void push_record(const LiftArgs& A, int b) {
+  if (A.n_peer == 0) return;
+  const float4* src = reinterpret_cast<const float4*>(A.out + b);
+  float4 w[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) w[i] = src[i];
+  for (int p = 0; p < A.n_peer; ++p) {
+    float4* dst = reinterpret_cast<float4*>(A.peer[p] + A.peer_off + b);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = w[i];
+  }
+}
 
 struct Rect {
   int x0, y0, x1, y1, w, h;

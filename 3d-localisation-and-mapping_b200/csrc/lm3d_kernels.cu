@@ -11,8 +11,8 @@
 //                            the target bins in pass 2, exact select                              (lm3d_lift_quad.cuh)
 //      lift_resolve_kernel : the boxes pass 1 / 2 could not resolve (ties), exact key-space select (lm3d_lift_quad.cuh)
 //   4. lift_block_kernel   : persistent, ONE CTA PER BOX, the same scheme at block scope          (lm3d_lift_block.cuh)
-//   5. tile pyramid        : large frames whose CTA-class boxes cover them at least once: tile_map / tile_build /
-//                            tile_box kernels per chunk of frames, before lift_block_kernel      (lm3d_lift_tiles.cuh)
+//   5. tile path           : large frames whose CTA-class boxes cover them at least once: tile_sum_kernel (per-tile
+//                            summaries) + tile_box_kernel per chunk of frames, before lift_block_kernel (lm3d_lift_tiles.cuh)
 // Alternative kernels kept for A/B runs and odd shapes: lm3d_lift_tma.cuh, lm3d_lift_hist.cuh, lm3d_lift_large.cuh;
 // shared warp helpers in lm3d_warp_util.cuh.  The kernels live in .cuh parts that are included here, in order, into ONE translation unit
 // (one nvcc invocation, no relocatable device code); the host side of the C ABI follows below.
@@ -116,8 +116,6 @@ static int device_info(DeviceInfo** out) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tile_ctas, tile_box_kernel, kBlkThreads, kTileBoxSmemWords * 4);
     if (e != cudaSuccess) return (int)e;
     d.tile_ctas = std::max(d.tile_ctas, 1);
-    e = cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBuildSmemWords * 4);
-    if (e != cudaSuccess) return (int)e;
     d.large_ctas = std::max(d.large_ctas, 1);
     d.attrs_set = true;
   }
@@ -180,19 +178,19 @@ static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, 
   return span;
 }
 
-// Tile-pyramid path (lm3d_lift_tiles.cuh): scratch that follows the base workspace.  The path is taken when the
+// Tile path (lm3d_lift_tiles.cuh): scratch that follows the base workspace.  The path is taken when the
 // frames are large enough to pay for a per-frame pass (H*W >= 2^18; LM3D_TILE_PATH=on forces it for any frame of at
 // least one tile, =off disables it), W % 4 == 0 and the caller's workspace holds the scratch of at least one frame.
 struct TilePlan {
   bool on = false;
   int ntx = 0, nty = 0, chunk = 0, n_chunks = 0;
   uint32_t area_thr = 1;
-  size_t off_area = 0, off_cursor = 0, off_map = 0, off_sum = 0, off_cdf = 0, off_sorted = 0, bytes = 0;  // relative to the base size
+  size_t off_area = 0, off_cursor = 0, off_sum = 0, bytes = 0;  // relative to the base size
 };
 static int tile_chunk_default() {
   const char* env = getenv("LM3D_TILE_CHUNK");
   const int v = env ? atoi(env) : 0;
-  return v > 0 ? v : 16;
+  return v > 0 ? v : 64;
 }
 static bool tile_plan(int64_t F, int32_t H, int32_t W, size_t avail, int want_chunk, TilePlan* P) {
   *P = TilePlan();
@@ -202,14 +200,13 @@ static bool tile_plan(int64_t F, int32_t H, int32_t W, size_t avail, int want_ch
   if ((W & 3) != 0 || F < 1) return false;
   if (!force && (int64_t)H * W < ((int64_t)1 << 18)) return false;
   if (H < kTile || W < kTile) return false;
-  P->ntx = (W + kTile - 1) / kTile;
-  P->nty = (H + kTile - 1) / kTile;
-  const size_t nt = (size_t)P->ntx * P->nty;
-  const size_t per_frame = align_up(nt * sizeof(TileSum), 256) + align_up(nt * kTileBins * 2, 256) + align_up(nt * kTilePix * 4, 256);
+  P->ntx = W / kTile;  // complete tiles only: the partial tiles at the right / bottom edge stay strip pixels
+  P->nty = H / kTile;
+  const size_t per_frame = align_up((size_t)P->ntx * P->nty * sizeof(TileSum), 256);
   int64_t chunk = std::min<int64_t>(F, want_chunk);
   auto total = [&](int64_t c) {
     const int64_t nc = (F + c - 1) / c;
-    return align_up((size_t)F * 4, 256) + align_up((size_t)nc * 4, 256) + align_up((size_t)c * sizeof(TileMap), 256) + (size_t)c * per_frame;
+    return align_up((size_t)F * 4, 256) + align_up((size_t)nc * 4, 256) + (size_t)c * per_frame;
   };
   while (chunk >= 1 && total(chunk) > avail) chunk >>= 1;
   if (chunk < 1) return false;
@@ -218,10 +215,7 @@ static bool tile_plan(int64_t F, int32_t H, int32_t W, size_t avail, int want_ch
   size_t off = 0;
   P->off_area = off; off += align_up((size_t)F * 4, 256);
   P->off_cursor = off; off += align_up((size_t)P->n_chunks * 4, 256);
-  P->off_map = off; off += align_up((size_t)chunk * sizeof(TileMap), 256);
-  P->off_sum = off; off += (size_t)chunk * align_up(nt * sizeof(TileSum), 256);
-  P->off_cdf = off; off += (size_t)chunk * align_up(nt * kTileBins * 2, 256);
-  P->off_sorted = off; off += (size_t)chunk * align_up(nt * kTilePix * 4, 256);
+  P->off_sum = off; off += (size_t)chunk * per_frame;
   P->bytes = off;
   double cover = 1.0;
   if (const char* c = getenv("LM3D_TILE_COVER")) cover = atof(c);
@@ -323,11 +317,16 @@ int lm3d_scale_boxes(const double* boxes_xyxy, const double* image_wh, const int
   return (int)cudaGetLastError();
 }
 
-int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7, const double* intr4,
-                    const int32_t* rect4, const int64_t* frame_off, int64_t B, double scale_depth,
-                    double max_depth_mm, double q_percent, lm3d_box_out* out, float* order_stats, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+static int lift_boxes_impl(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7, const double* intr4,
+                           const int32_t* rect4, const int64_t* frame_off, int64_t B, double scale_depth,
+                           double max_depth_mm, double q_percent, lm3d_box_out* out, float* order_stats, void* workspace,
+                           size_t workspace_bytes, void* const* peer_out, int n_peers, int64_t box_offset, void* stream) {
   if (F < 0 || B < 0 || H < 1 || W < 1) return LM3D_ERR_BAD_ARG;
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_out) || box_offset < 0) return LM3D_ERR_BAD_ARG;
+  for (int p = 0; p < n_peers; ++p)
+    if (!peer_out[p] || ((uintptr_t)peer_out[p] & 15) != 0) return LM3D_ERR_BAD_ARG;
   if (!(q_percent >= 0.0 && q_percent <= 100.0)) return LM3D_ERR_BAD_ARG;
   if (!(scale_depth > 0.0)) return LM3D_ERR_BAD_ARG;
   if (B == 0) return LM3D_OK;
@@ -346,14 +345,14 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   workspace_layout(F, B, (char*)workspace, &ws);
   cudaError_t e = cudaMemsetAsync(ws.counters, 0, 128, st);
   if (e != cudaSuccess) return (int)e;
-  // tile-pyramid path: uses whatever the caller's workspace holds beyond the base layout (lm3d_lift_workspace_bytes
+  // tile path: uses whatever the caller's workspace holds beyond the base layout (lm3d_lift_workspace_bytes
   // sizes it for the default chunk of frames; a smaller workspace means smaller chunks or, below one frame, no tiles)
   TilePlan TP;
   char* tile_base = (char*)workspace + base_bytes;
   uint32_t* frame_area = nullptr;
   if (tile_plan(F, H, W, workspace_bytes - base_bytes, tile_chunk_default(), &TP)) {
     frame_area = (uint32_t*)(tile_base + TP.off_area);
-    e = cudaMemsetAsync(frame_area, 0, TP.off_map - TP.off_area, st);  // frame areas + chunk cursors
+    e = cudaMemsetAsync(frame_area, 0, TP.off_sum - TP.off_area, st);  // frame areas + chunk cursors
     if (e != cudaSuccess) return (int)e;
   }
 
@@ -385,6 +384,8 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   A.quant = q_percent / 100.0;
   A.scale_depth = scale_depth;
   A.out = out; A.order_stats = order_stats;
+  A.n_peer = n_peers; A.peer_off = box_offset;
+  for (int p = 0; p < 8; ++p) A.peer[p] = p < n_peers ? (lm3d_box_out*)peer_out[p] : nullptr;
 
   // persistent grids: a multiple of the SM count, capped by the amount of work
   if (tma_span > 0) {
@@ -419,27 +420,22 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
 #endif
   prof_mark(4, st);
   if (TP.on) {
-    // frame chunks: bin map -> tiles -> boxes.  What a chunk's boxes cannot resolve lands on the CTA-per-box list.
+    // frame chunks: tile summaries -> boxes.  What a chunk's boxes cannot resolve lands on the CTA-per-box list.
     TileArgs T;
     T.A = A;
     T.A.list = ws.large_list;
-    T.frame_off = frame_off; T.frame_area = frame_area; T.area_thr = TP.area_thr; T.F = F;
+    T.frame_off = frame_off; T.frame_area = frame_area; T.area_thr = TP.area_thr;
     T.ntx = TP.ntx; T.nty = TP.nty;
-    T.map = (TileMap*)(tile_base + TP.off_map);
     T.tsum = (TileSum*)(tile_base + TP.off_sum);
-    T.tcdf = (uint16_t*)(tile_base + TP.off_cdf);
-    T.tsorted = (uint32_t*)(tile_base + TP.off_sorted);
     const int n_tiles = TP.ntx * TP.nty;
     const unsigned box_grid = (unsigned)((int64_t)dev->sms * dev->tile_ctas);
     for (int c = 0; c < TP.n_chunks; ++c) {
       T.f0 = c * TP.chunk;
       T.nf = (int)std::min<int64_t>(TP.chunk, F - T.f0);
       T.cursor = (int32_t*)(tile_base + TP.off_cursor) + c;
-      tile_map_kernel<<<T.nf, kLargeThreads, 0, st>>>(T);
-      tile_build_kernel<<<dim3((unsigned)((n_tiles + kTileBuildWarps - 1) / kTileBuildWarps), (unsigned)T.nf), kTileBuildWarps * 32,
-                          kTileBuildSmemWords * 4, st>>>(T);
+      tile_sum_kernel<<<dim3((unsigned)((n_tiles + kTileSumThreads - 1) / kTileSumThreads), (unsigned)T.nf), kTileSumThreads, 0, st>>>(T);
       tile_box_kernel<<<box_grid, kBlkThreads, kTileBoxSmemWords * 4, st>>>(T);
-      g_launches += 3;
+      g_launches += 2;
     }
   }
 #ifdef LM3D_DEBUG_BOUNDS
@@ -465,6 +461,44 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
   g_prof_valid = g_profile;
   return (int)cudaGetLastError();
 }
+
+extern "C" {
+
+int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7, const double* intr4,
+                    const int32_t* rect4, const int64_t* frame_off, int64_t B, double scale_depth,
+                    double max_depth_mm, double q_percent, lm3d_box_out* out, float* order_stats, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return lift_boxes_impl(depth, F, H, W, pose7, intr4, rect4, frame_off, B, scale_depth, max_depth_mm, q_percent, out,
+                         order_stats, workspace, workspace_bytes, nullptr, 0, 0, stream);
+}
+
+int lm3d_lift_boxes_gather(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7, const double* intr4,
+                           const int32_t* rect4, const int64_t* frame_off, int64_t B, double scale_depth,
+                           double max_depth_mm, double q_percent, lm3d_box_out* out, float* order_stats, void* workspace,
+                           size_t workspace_bytes, void* const* peer_out, int32_t n_peers, int64_t box_offset, void* stream) {
+  return lift_boxes_impl(depth, F, H, W, pose7, intr4, rect4, frame_off, B, scale_depth, max_depth_mm, q_percent, out,
+                         order_stats, workspace, workspace_bytes, peer_out, n_peers, box_offset, stream);
+}
+
+// Gather buffers: plain cudaMalloc (an IPC handle names the allocation's base, so the buffer must BE an allocation, not a
+// slice of a caching allocator's block) + the CUDA IPC plumbing to map a peer process's buffer into this one.
+int lm3d_gather_alloc(size_t bytes, void** dev_ptr, void* ipc_handle64) {
+  if (!dev_ptr || !ipc_handle64 || bytes == 0) return LM3D_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle64, *dev_ptr);
+  if (e != cudaSuccess) { cudaFree(*dev_ptr); *dev_ptr = nullptr; return (int)e; }
+  return LM3D_OK;
+}
+int lm3d_gather_open(const void* ipc_handle64, void** dev_ptr) {
+  if (!dev_ptr || !ipc_handle64) return LM3D_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int lm3d_gather_close(void* dev_ptr) { return dev_ptr ? (int)cudaIpcCloseMemHandle(dev_ptr) : LM3D_ERR_BAD_ARG; }
+int lm3d_gather_free(void* dev_ptr) { return dev_ptr ? (int)cudaFree(dev_ptr) : LM3D_ERR_BAD_ARG; }
 
 int lm3d_ingest_depth(const void* raw_8uc4, int64_t n_pixels, float scale, float* depth_out, void* stream) {
   if (n_pixels < 0) return LM3D_ERR_BAD_ARG;

@@ -13,6 +13,10 @@ namespace lm3d {
 //     map cannot split go to the bisection select of 4.  Needs W % 4 == 0.
 // ------------------------------------------------------------------------------------------
 constexpr int kBlkThreads = 256, kBlkWarps = 8;
+#ifndef LM3D_BLK_BATCH
+#define LM3D_BLK_BATCH 8   // row steps whose loads a thread issues together (0: the two-deep cp.async pipeline of lift_quad)
+#endif
+constexpr int kBlkBatch = LM3D_BLK_BATCH ? LM3D_BLK_BATCH : 1;
 constexpr int kBlkBins = 1024;                   // bracket bins (1000 span the bracket): 4 per thread
 constexpr int kBlkHistWords = 256 + kBlkBins + 256;  // [0,256) below, [256,1280) bracket bins, [1280,1536) above (thread-private)
 constexpr int kBlkCollRows = 16;                 // thread-private column depth (+4 guard rows)
@@ -143,6 +147,26 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
       const int rows_l = rc.h - row_l;
       uint32_t no_cptr = 0u;
       acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
+#if LM3D_BLK_BATCH
+      // the loads of kBlkBatch row steps are issued together (registers): a two-deep cp.async pipeline costs one
+      // memory round trip per pair of steps, and the CTA kernel is bound by exactly that
+#pragma unroll 1
+      for (int st = 0; st < nsteps; st += kBlkBatch) {
+        uint4 qb[kBlkBatch];
+#pragma unroll
+        for (int i = 0; i < kBlkBatch; ++i) {
+          qb[i] = make_uint4(0u, 0u, 0u, 0u);
+          if ((st + i) * RPq < rows_l) qb[i] = ldg_u4(gp + (size_t)i * rstep);
+        }
+        gp += (size_t)kBlkBatch * rstep;
+#pragma unroll
+        for (int i = 0; i < kBlkBatch; ++i) {
+          if (st + i >= nsteps) break;
+          accum_quad_hist<false>(qb[i], dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, 0u, 0u, no_cptr);
+          vr += frp;
+        }
+      }
+#else
 #pragma unroll
       for (int i = 0; i < kQuadDepth; ++i) {
         cp_async_16(pipe_s + i * kSlot, gp, (i * RPq < rows_l) ? 16u : 0u);
@@ -166,6 +190,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
         }
       }
       cp_async_wait<0>();
+#endif
       const float du = (float)col0 - uc;
       su = fmaf(du, acc.s0[0], fmaf(du + 1.f, acc.s0[1], fmaf(du + 2.f, acc.s0[2], fmaf(du + 3.f, acc.s0[3], su))));
       s0_all += (acc.s0[0] + acc.s0[1]) + (acc.s0[2] + acc.s0[3]);
@@ -287,6 +312,24 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
           const int row_l = lane_ok ? tr : 0;
           const float* gp = fbase + (uint32_t)((rc.y0 + row_l) * W + col0);
           const int rows_l = rc.h - row_l;
+#if LM3D_BLK_BATCH
+#pragma unroll 1
+          for (int st = 0; st < nsteps; st += kBlkBatch) {
+            uint4 qb[kBlkBatch];
+#pragma unroll
+            for (int i = 0; i < kBlkBatch; ++i) {
+              qb[i] = make_uint4(0u, 0u, 0u, 0u);
+              if ((st + i) * RPq < rows_l) qb[i] = ldg_u4(gp + (size_t)i * rstep);
+            }
+            gp += (size_t)kBlkBatch * rstep;
+#pragma unroll
+            for (int i = 0; i < kBlkBatch; ++i) {
+              if (st + i >= nsteps) break;
+              collect_quad<kBlkThreads * 4>(qb[i], s4f, kkf, tg, dt, cptr);
+              cptr = min(cptr, cend);
+            }
+          }
+#else
 #pragma unroll
           for (int i = 0; i < kQuadDepth; ++i) {
             cp_async_16(pipe_s + i * kSlot, gp, (i * RPq < rows_l) ? 16u : 0u);
@@ -310,6 +353,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
             }
           }
           cp_async_wait<0>();
+#endif
         }
         if (cptr >= cend) sh.overflow = 1;
         __syncthreads();
@@ -371,9 +415,11 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
         done = true;
       }
     }
-    if (tid == 0)
+    if (tid == 0) {
       write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr, tb,
                    rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
+      push_record(A, b);
+    }
   }
 }
 

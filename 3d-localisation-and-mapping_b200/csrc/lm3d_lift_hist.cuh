@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kHistWarps * 32, LM3D_HIST_MINB) lift_hist_ker
         write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
                          tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
                          (float)(1.0 / A.scale_depth));
+        push_record(A, b);
       }
       __syncwarp();
     }

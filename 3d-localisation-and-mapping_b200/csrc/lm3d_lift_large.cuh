@@ -297,9 +297,11 @@ __global__ void __launch_bounds__(kLargeThreads) lift_large_kernel(const LiftArg
         block_select_window(src, wlo, whi, below, cnt, r, two, sortbuf, sh, k0, k1);
       }
     }
-    if (tid == 0)
+    if (tid == 0) {
       write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr, tb,
                    rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
+      push_record(A, b);
+    }
   }
 }
 

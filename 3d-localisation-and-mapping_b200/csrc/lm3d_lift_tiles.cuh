@@ -1,69 +1,69 @@
-// lm3d_lift_tiles.cuh -- section 5: the TILE PYRAMID path for large frames with heavily overlapping boxes (C3 / C5).
+// lm3d_lift_tiles.cuh -- section 5: the TILE path for large frames with heavily overlapping boxes (C3 / C5).
 // Part of the single translation unit lm3d_kernels.cu (included there, in order); not a stand-alone header.
 //
-// One CTA per box (lift_block_kernel) touches every pixel of a frame once per covering box: 3.1x (C3) to 16.3x (C5).
-// Here a frame is read ONCE, tile by tile (32 x 32 pixels), and every box that covers a tile completely takes the
-// tile's precomputed summary instead of its 1024 pixels:
+// One CTA per box (lift_block_kernel) pays the full per-pixel price -- validity, unproject + pose, six min / max,
+// three sums, a histogram update, and a second visit for the percentile -- for every pixel of every box: 3.1x (C3)
+// to 16.3x (C5) per frame pixel.  Here the box-independent part of that work is done ONCE per frame pixel:
 //
-//   tile_map_kernel    per frame: 4096-pixel lattice sample -> a MONOTONE fp32 bin map for the whole frame
-//                      (254 linear bins between the sample's 1 % and 99 % points +- 10 %, one catch-all either side)
-//   tile_build_kernel  per tile (one warp): validity, unproject + pose, per-axis min / max, sums, count  -> TileSum (48 B);
-//                      256-bin histogram of the tile under the frame map -> inclusive prefix (u16 x 256, 512 B);
-//                      the tile's valid keys counting-sorted by bin -> 4 KB  (keys of bin b = one contiguous run)
-//   tile_box_kernel    per box (one CTA): boundary strips (the part of the rect outside fully covered tiles, <= 31
-//                      pixels wide) go through the same per-pixel pass as lift_block_kernel; interior tiles add their
-//                      summaries and histograms; the bins of the target ranks are read off the combined histogram;
-//                      their keys come from the tiles' bin-sorted runs (+ a second pass over the strips) and an exact
-//                      radix select finishes.  Per-pixel work drops to the strips: ~15 % of a C3 / C5 box.
+//   tile_sum_kernel   per 16 x 16 tile (a warp per 32 x 32 block): count, sums, per-axis world min / max and the
+//                     smallest / largest valid depth of the tile -> TileSum (64 B per 1 KB of pixels).  Registers
+//                     only: no shared memory, no atomics.
+//   tile_box_kernel   per box (one CTA), the scheme of lift_block_kernel with the interior taken from the tiles:
+//                       * boundary strips (the part of the rect outside completely covered tiles, < 16 px wide) are
+//                         walked pixel by pixel as before;
+//                       * a completely covered tile contributes its sums / min / max / count from its TileSum;
+//                       * for the percentile, a tile whose depth range lies entirely under (over) the box's
+//                         bracket is counted (ignored) without touching its pixels; only tiles that straddle
+//                         the bracket are scanned, with a light pass (validity + histogram update, 7 instructions
+//                         per pixel instead of 23) and, for the second pass, one compare per pixel.
+//                     On the C3 / C5 law (a flat sign patch in front of a tilted plane) the scanned tiles are the
+//                     patch, ~40 % of a box.
 //
-// Exactness: bins are a fixed monotone function of the depth bits, evaluated by the same fma in all three kernels,
-// so "key is in bin b" is the same set everywhere and the two order statistics come back bit-exactly.  A box whose
-// target rank falls into a catch-all bin, or whose target bins hold more than kTileCollCap keys (heavy ties), is
-// appended to the CTA-per-box list and finished by lift_block_kernel (which never fails).
+// Exactness: identical to lift_block_kernel -- the bracket histogram is the same monotone fp32 map evaluated by the
+// same fma in both passes, the selected order statistics are bit-exact.  A box whose bracket misses the rank or whose
+// target bins overflow the collect buffer is appended to the CTA-per-box list and finished by lift_block_kernel.
+//
+// (Round 2 first built a heavier pyramid -- a per-frame bin map, per-tile 256-bin prefix histograms and bin-sorted
+// copies of every tile, so that a box could read its percentile bins off the tiles.  It was exact and parity-green
+// but no faster than one CTA per box: building it cost 65 instructions per frame pixel, and the flat sign patches
+// put tens of thousands of keys into one or two bins, which then had to be streamed again per box.  DESIGN.md 4.4.)
 #ifndef LM3D_LIFT_TILES_CUH_
 #define LM3D_LIFT_TILES_CUH_
 
 namespace lm3d {
 
-constexpr int kTile = 32;                    // tile edge in pixels
-constexpr int kTilePix = kTile * kTile;
-constexpr int kTileBins = 256;               // bin 0 / 255: catch-alls below / above the frame map, 1..254 linear
-constexpr int kTileWordBin1 = 256;           // histogram word of bin 1 (words below it: private "below / invalid" words)
-constexpr int kTileWordAbove = kTileWordBin1 + (kTileBins - 2);  // first private "above" word (510)
-constexpr int kTileWarpHistWords = 320;      // warp histogram in tile_build: words [224, 542) of the map -> 318 used
-constexpr int kTileBuildWarps = 8;
-constexpr int kTileBuildSmemWords = kTileBuildWarps * (kTileWarpHistWords + kTilePix);
-constexpr int kTileSample = 4096;            // lattice sample per frame (block bitonic sort)
-constexpr int kTileCollCap = 8192;           // keys of the target bins a box may collect
-constexpr int kTileSampleCap = kTileCollCap / 2;  // level-2 sample (two copies share the collect buffer)
-constexpr int kTileBoxHistWords = 256 + (kTileBins - 2) + 256;  // 766: private below | bins 1..254 | private above
-constexpr int kTileBoxSmemWords = 768 + kTileCollCap + 256 + kBlkThreads * 4 * kQuadDepth;
+constexpr int kTile = 16;                    // tile edge in pixels
+constexpr int kTileQuads = kTile * kTile / 4;  // float4 quads per tile (64)
+constexpr int kTileMaxInt = 4096;            // completely covered tiles per box the scan list holds
+constexpr int kTileCollCap = 2048;           // keys of the target bins a box may collect
+#ifndef LM3D_TILE_SAMPLE
+#define LM3D_TILE_SAMPLE 512
+#endif
+constexpr int kTileSample = LM3D_TILE_SAMPLE;  // lattice sample per box
+#ifndef LM3D_TILE_BATCH
+#define LM3D_TILE_BATCH 4
+#endif
+constexpr int kTileBatch = LM3D_TILE_BATCH;    // loads a thread issues together (strip row steps, tile quads)
+constexpr int kTileHistWords = 256 + kBlkBins + 256;
+constexpr int kTileBoxSmemWords = kTileHistWords + kSortCap + kTileMaxInt;
 
-struct __align__(16) TileSum {   // 48 bytes
+struct __align__(16) TileSum {   // 64 bytes
   int32_t n_valid;
   float s0, su, sv;              // sum d, sum (u - uc_t) d, sum (v - vc_t) d over the tile's valid pixels (tile-centred)
   float mn[3], mx[3];            // min / max of d (a_k u + b_k v + c_k)
-  float pad[2];
+  float dmin, dmax;              // smallest / largest valid depth (+inf / -inf when the tile has none)
+  float pad[4];
 };
-static_assert(sizeof(TileSum) == 48, "TileSum layout");
-
-struct __align__(16) TileMap {   // per frame slot
-  float s4f, kkf;                // word(d) = bits(clamp(fma(d, s4f, kkf))) - bits(2^25)
-  int32_t tiled, pad;
-};
+static_assert(sizeof(TileSum) == 64, "TileSum layout");
 
 struct TileArgs {
   LiftArgs A;
   const int64_t* frame_off;
   const uint32_t* frame_area;    // [F] large-box area per frame in units of 1024 px
   uint32_t area_thr;             // frame takes the tile path iff frame_area >= area_thr
-  int64_t F;
   int f0, nf;                    // frame chunk [f0, f0 + nf)
-  int ntx, nty;                  // tiles per row / column of a frame
-  TileMap* map;                  // [chunk]
+  int ntx, nty;                  // COMPLETE tiles per row / column of a frame (partial edge tiles are strip pixels)
   TileSum* tsum;                 // [chunk][nty*ntx]
-  uint16_t* tcdf;                // [chunk][nty*ntx][256]
-  uint32_t* tsorted;             // [chunk][nty*ntx][1024]
   int32_t* cursor;               // this chunk's box cursor (zeroed by the caller)
 };
 
@@ -78,284 +78,93 @@ __device__ __forceinline__ FrameTab load_tab(const FrameTab* tab, int f) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 5a. frame bin map
+// 5a. tile summaries: a THREAD per tile (a warp = 32 neighbouring tiles of one tile row).  No cross-lane reduction at
+//     all: the first version gave a warp a 32 x 32 block and spent more instructions on the segmented shuffle /
+//     REDUX reductions and per-half setup than on the pixels (36 per pixel, issue-bound at 5.6 us per 1920 x 1440
+//     frame).  A lane's 16-byte loads sit 64 bytes from its neighbours': every sector fetched is used by the lane's
+//     next three loads (L1), DRAM traffic is the frame once.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kLargeThreads) tile_map_kernel(const TileArgs T) {
-  __shared__ uint32_t sortbuf[kTileSample];
-  __shared__ LargeShared sh;
-  const int slot = blockIdx.x, f = T.f0 + slot, tid = threadIdx.x;
-  const bool tiled = T.frame_area[f] >= T.area_thr;
-  if (!tiled) {
-    if (tid == 0) { TileMap m; m.s4f = 0.f; m.kkf = 0.f; m.tiled = 0; m.pad = 0; T.map[slot] = m; }
-    return;
-  }
-  const int H = T.A.H, W = T.A.W;
-  const long long n_pix = (long long)H * W;
-  const float* __restrict__ fbase = T.A.depth + (size_t)f * H * W;
-  int svl = 0;
-  for (int i = tid; i < kTileSample; i += kLargeThreads) {
-    const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / kTileSample;
-    const uint32_t bits = __float_as_uint(__ldg(fbase + idx));
-    const bool v = key_valid(bits, T.A.dmax_bits);
-    sortbuf[i] = v ? bits : kKeyInvalid;
-    svl += v;
-  }
-  const int sv = block_sum_i(svl, sh, 0);
-  block_bitonic(sortbuf, kTileSample);
-  if (tid == 0) {
-    TileMap m;
-    m.tiled = 1; m.pad = 0;
-    float lo = 1.f, hi = 2.f;
-    if (sv > 0) {
-      lo = __uint_as_float(sortbuf[sv / 100]);
-      hi = __uint_as_float(sortbuf[sv - 1 - sv / 100]);
-    }
-    const float wd = hi - lo, mg = 0.1f * wd + 1e-3f * hi;
-    lo = fmaxf(lo - mg, 1e-30f);
-    hi = fminf(hi + mg, 3.0e38f);
-    const float span = hi - lo;
-    m.s4f = (span > 0.f && span < 3.0e38f) ? fminf(4.f * (float)(kTileBins - 2) / span, 2097152.f / hi) : 0.f;
-    m.kkf = fmaf(-lo, m.s4f, 33554432.f + 4.f * (float)kTileWordBin1);
-    T.map[slot] = m;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// 5b. tile build: one warp per tile.  Lane l owns quad column (l & 7) of rows (l >> 3) + 4 s, s = 0..7.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileBuildWarps * 32, 2) tile_build_kernel(const TileArgs T) {
-  extern __shared__ __align__(16) uint32_t smem_u32[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+constexpr int kTileSumThreads = 128;
+__global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArgs T) {
   const int slot = blockIdx.y, f = T.f0 + slot;
-  const TileMap fm = T.map[slot];
-  if (!fm.tiled) return;
-  const int tile = blockIdx.x * kTileBuildWarps + wib;
+  if (T.frame_area[f] < T.area_thr) return;  // frame under the cover threshold: lift_block_kernel has its boxes
   const int n_tiles = T.ntx * T.nty;
+  const int tile = blockIdx.x * kTileSumThreads + threadIdx.x;
   if (tile >= n_tiles) return;
-  uint32_t* hist = smem_u32 + wib * (kTileWarpHistWords + kTilePix);  // word w of the map lives at hist[w - 224]
-  uint32_t* stage = hist + kTileWarpHistWords;
-  const int H = T.A.H, W = T.A.W;
+  const int W = T.A.W;
   const int ty = tile / T.ntx, tx = tile - ty * T.ntx;
-  const float* __restrict__ fbase = T.A.depth + (size_t)f * H * W;
+  const float* __restrict__ p = T.A.depth + (size_t)f * T.A.H * W + (size_t)(ty * kTile) * W + tx * kTile;
   const FrameTab tb = load_tab(T.A.tab, f);
-
+  const float uc = (float)(tx * kTile) + 7.5f, vc = (float)(ty * kTile) + 7.5f;
+  float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+  float dmn = INFINITY, dmx = -INFINITY, s0 = 0.f, su = 0.f, sv = 0.f, nv = 0.f;
+  // ray term of pixel (u, v): g_k = a_k u + b_k v + c_k, walked along a row in pairs: (g, g + a_k) += 2 a_k
+  const f32x2 step0 = pack2(2.f * tb.a[0], 2.f * tb.a[0]), step1 = pack2(2.f * tb.a[1], 2.f * tb.a[1]), step2 = pack2(2.f * tb.a[2], 2.f * tb.a[2]);
+  const float u0 = (float)(tx * kTile);
+#pragma unroll 1
+  for (int r0 = 0; r0 < kTile; r0 += 2) {  // two rows = eight 16-byte loads in flight
+    uint4 q[8];
 #pragma unroll
-  for (int i = 0; i < kTileWarpHistWords / 32; ++i) hist[i * 32 + lane] = 0u;
-  __syncwarp();
-
-  const int col0 = tx * kTile + 4 * (lane & 7);
-  const int row0 = ty * kTile + (lane >> 3);
-  uint32_t dm[4];
+    for (int i = 0; i < 8; ++i) q[i] = ldg_u4(p + (size_t)(r0 + (i >> 2)) * W + (i & 3) * 4);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) dm[j] = (col0 + j < W) ? T.A.dmax_bits : 0u;
-  const float uc = (float)(tx * kTile) + 15.5f, vc = (float)(ty * kTile) + 15.5f;
-  f32x2 cA[3], cB[3];
-  {
-    const float uf = (float)col0;
+    for (int rr = 0; rr < 2; ++rr) {
+      const float vf = (float)(ty * kTile + r0 + rr);
+      const float vr = vf - vc;
+      const float b0 = fmaf(tb.b[0], vf, fmaf(tb.a[0], u0, tb.c[0])), b1 = fmaf(tb.b[1], vf, fmaf(tb.a[1], u0, tb.c[1])),
+                  b2 = fmaf(tb.b[2], vf, fmaf(tb.a[2], u0, tb.c[2]));
+      f32x2 g0 = pack2(b0, b0 + tb.a[0]), g1 = pack2(b1, b1 + tb.a[1]), g2 = pack2(b2, b2 + tb.a[2]);
+      float du = u0 - uc;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float ck = fmaf(tb.b[k], vc, fmaf(tb.a[k], uf, tb.c[k]));
-      cA[k] = pack2(ck, ck + tb.a[k]);
-      cB[k] = pack2(fmaf(2.f, tb.a[k], ck), fmaf(3.f, tb.a[k], ck));
-    }
-  }
-  // all eight quads of the lane are requested before the first is reduced (32 rows x 128 B in flight per warp)
-  uint4 q[8];
-  const bool col_ok = col0 < W;  // (W % 4 == 0: a quad is inside the frame or outside it)
+      for (int qi = 0; qi < 4; ++qi) {
+        const uint4 qq = q[rr * 4 + qi];
+        const uint32_t bits[4] = {qq.x, qq.y, qq.z, qq.w};
+        float d[4];
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const int row = row0 + 4 * s;
-    q[s] = make_uint4(0u, 0u, 0u, 0u);
-    if (col_ok && row < H) q[s] = ldg_u4(fbase + (size_t)row * W + col0);
-  }
-  const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-  const uint32_t hist_bias = hist_s - 0x30000000u - 224u * 4u;
-  const float ylo = 33554432.f + 4.f * (float)(224 + lane), yhi = 33554432.f + 4.f * (float)(kTileWordAbove + lane);
-  AccQ acc;
-  acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
-  acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
-  acc.sv = 0.f; acc.n_valid = 0.f;
-  acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
-  uint32_t no_cptr = 0u;
-  float vr = (float)row0 - vc;
+        for (int j = 0; j < 4; ++j) {
+          const bool v = key_valid(bits[j], T.A.dmax_bits);
+          d[j] = __uint_as_float(v ? bits[j] : 0x7fffffffu);  // NaN: dropped by the 3-input min / max
+          if (v) { nv += 1.0f; s0 += __uint_as_float(bits[j]); su = fmaf(du + (float)j, __uint_as_float(bits[j]), su); sv = fmaf(vr, __uint_as_float(bits[j]), sv); }
+        }
+        du += 4.f;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    accum_quad_hist<false>(q[s], dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, fm.s4f, fm.kkf, ylo, yhi, hist_bias, acc, 0u, 0u, no_cptr);
-    vr += 4.f;
-  }
-  const float du = (float)col0 - uc;
-  const float su_l = fmaf(du, acc.s0[0], fmaf(du + 1.f, acc.s0[1], fmaf(du + 2.f, acc.s0[2], (du + 3.f) * acc.s0[3])));
-  const float s0_l = (acc.s0[0] + acc.s0[1]) + (acc.s0[2] + acc.s0[3]);
-  const int n_valid = warp_sum_i((int)acc.n_valid);
-  {
-    const float S0 = warp_sum_f(s0_l), SU = warp_sum_f(su_l), SV = warp_sum_f(acc.sv);
-    const float m0 = warp_min_f(acc.mn0), m1 = warp_min_f(acc.mn1), m2 = warp_min_f(acc.mn2);
-    const float x0 = warp_max_f(acc.mx0), x1 = warp_max_f(acc.mx1), x2 = warp_max_f(acc.mx2);
-    if (lane == 0) {
-      float4* o = reinterpret_cast<float4*>(T.tsum + (size_t)slot * n_tiles + tile);
-      o[0] = make_float4(__int_as_float(n_valid), S0, SU, SV);
-      o[1] = make_float4(m0, m1, m2, x0);
-      o[2] = make_float4(x1, x2, 0.f, 0.f);
-    }
-  }
-  __syncwarp();
-  // ---- bin counts -> inclusive prefix.  Lane l owns bins 8 l .. 8 l + 7; bin 0 = valid keys under the map
-  //      (private words minus the slots that were not valid pixels), bin 255 = keys above it ------------------
-  int c[8];
-  {
-    const int below_all = warp_sum_i((int)hist[lane]);                            // words 224 .. 255
-    const int above_all = warp_sum_i((int)hist[kTileWordAbove - 224 + lane]);    // words 510 .. 541
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int bin = 8 * lane + i;
-      c[i] = (bin >= 1 && bin <= kTileBins - 2) ? (int)hist[kTileWordBin1 - 224 + bin - 1] : 0;
-    }
-    if (lane == 0) c[0] = below_all - (kTilePix - n_valid);
-    if (lane == 31) c[7] = above_all;
-  }
-  int tot = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot += c[i];
-  int incl = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(kFull, incl, o);
-    if (lane >= o) incl += t;
-  }
-  __syncwarp();  // every lane has read its histogram words: the region becomes the scatter cursors
-  {
-    int run = incl - tot;  // keys in bins before this lane's
-    uint32_t pk[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hist[8 * lane + i] = (uint32_t)run;  // exclusive offset = scatter cursor of the bin
-      run += c[i];
-      if (i & 1) pk[i >> 1] |= (uint32_t)run << 16; else pk[i >> 1] = (uint32_t)run;
-    }
-    reinterpret_cast<uint4*>(T.tcdf + ((size_t)slot * n_tiles + tile) * kTileBins)[lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
-  __syncwarp();
-  // ---- counting sort of the tile's valid keys by bin (order within a bin is arbitrary) -----------------------
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const uint32_t bits[4] = {q[s].x, q[s].y, q[s].z, q[s].w};
-    const bool row_ok = row0 + 4 * s < H;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (row_ok && key_valid(bits[j], dm[j])) {
-        const float yc = fminf(fmaxf(fmaf(__uint_as_float(bits[j]), fm.s4f, fm.kkf), 33554432.f + 4.f * 255.f), 33554432.f + 4.f * (float)kTileWordAbove);
-        const int bin = (int)(__float_as_uint(yc) - 0x4C000000u) - 255;  // word 255 -> bin 0, word 510 -> bin 255
-        const uint32_t pos = atomicAdd(&hist[bin], 1u);
-        stage[pos] = bits[j];
+        for (int h = 0; h < 2; ++h) {
+          const f32x2 dp = pack2(d[2 * h], d[2 * h + 1]);
+          float xa, xb;
+          unpack2(mul2(dp, g0), xa, xb); mn0 = fmin3(mn0, xa, xb); mx0 = fmax3(mx0, xa, xb);
+          unpack2(mul2(dp, g1), xa, xb); mn1 = fmin3(mn1, xa, xb); mx1 = fmax3(mx1, xa, xb);
+          unpack2(mul2(dp, g2), xa, xb); mn2 = fmin3(mn2, xa, xb); mx2 = fmax3(mx2, xa, xb);
+          g0 = add2(g0, step0); g1 = add2(g1, step1); g2 = add2(g2, step2);
+          dmn = fmin3(dmn, d[2 * h], d[2 * h + 1]);
+          dmx = fmax3(dmx, d[2 * h], d[2 * h + 1]);
+        }
       }
     }
   }
-  __syncwarp();
-  uint4* dst = reinterpret_cast<uint4*>(T.tsorted + ((size_t)slot * n_tiles + tile) * kTilePix);
-  const int n4 = (n_valid + 3) >> 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i * 32 + lane < n4) dst[i * 32 + lane] = reinterpret_cast<const uint4*>(stage)[i * 32 + lane];
+  float4* o = reinterpret_cast<float4*>(T.tsum + (size_t)slot * n_tiles + tile);
+  o[0] = make_float4(__int_as_float((int)nv), s0, su, sv);
+  o[1] = make_float4(mn0, mn1, mn2, mx0);
+  o[2] = make_float4(mx1, mx2, dmn, dmx);
 }
 
 // ------------------------------------------------------------------------------------------
-// 5c. exact select among m keys in shared memory by one CTA: radix-256 in key space, in place.
+// 5b. boxes: one CTA per box
 // ------------------------------------------------------------------------------------------
 struct TileBoxShared {
   LargeShared ls;
   double red_d[kBlkWarps][3];
   float red_f[kBlkWarps][6];
-  int red_i[kBlkWarps][2];
+  int red_i[kBlkWarps][4];
   int scan_w[kBlkWarps];
-  int b_lo, b_hi, before, end, ncoll, item, m_next, jb, jb1, below, keep;
-  uint32_t kmin, kmax;
+  int b_lo, b_hi, before, end, ncoll, item, n_scan;
 };
 
-__device__ void block_select_smem(uint32_t* buf, int m, int r, bool two, uint32_t* hist /* >= 768 words */, TileBoxShared& sh,
-                                  uint32_t& k0, uint32_t& k1) {
-  const int tid = threadIdx.x;
-  uint32_t* bmin = hist + 256;
-  uint32_t* bmax = hist + 512;
-  while (true) {
-    __syncthreads();
-    if (m <= 32) {
-      if (tid < 32) {
-        uint32_t s1[1] = {(tid < m) ? buf[tid] : kKeyInvalid};
-        warp_bitonic<1>(s1, tid);
-        const uint32_t a = __shfl_sync(kFull, s1[0], r), b = __shfl_sync(kFull, s1[0], two ? r + 1 : r);
-        if (tid == 0) { sh.kmin = a; sh.kmax = b; }
-      }
-      __syncthreads();
-      k0 = sh.kmin; k1 = sh.kmax;
-      __syncthreads();
-      return;
-    }
-    uint32_t mn = kKeyInvalid, mx = 0u;
-    for (int i = tid; i < m; i += kBlkThreads) { const uint32_t k = buf[i]; mn = min(mn, k); mx = max(mx, k); }
-    block_minmax_u(mn, mx, sh.ls);
-    if (mn >= mx) { k0 = k1 = mn; return; }
-    const uint32_t span = mx - mn;
-    const int shift = max(0, 24 - __clz(span));  // (span >> shift) <= 255
-    hist[tid] = 0u; bmin[tid] = 0xffffffffu; bmax[tid] = 0u;
-    if (tid == 0) { sh.jb = -1; sh.jb1 = -1; sh.m_next = 0; }
-    __syncthreads();
-    for (int i = tid; i < m; i += kBlkThreads) {
-      const uint32_t k = buf[i], bin = (k - mn) >> shift;
-      atomicAdd(&hist[bin], 1u);
-      atomicMin(&bmin[bin], k);
-      atomicMax(&bmax[bin], k);
-    }
-    __syncthreads();
-    // thread t owns bin t: block exclusive scan
-    const int cnt = (int)hist[tid];
-    int incl = cnt;
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) sh.scan_w[warp] = incl;
-    __syncthreads();
-    int wpre = 0;
-#pragma unroll
-    for (int w = 0; w < kBlkWarps; ++w) if (w < warp) wpre += sh.scan_w[w];
-    const int cum = wpre + incl - cnt;
-    const int r1 = r + (two ? 1 : 0);
-    if (r >= cum && r < cum + cnt) { sh.jb = tid; sh.below = cum; sh.keep = cnt; }
-    if (r1 >= cum && r1 < cum + cnt) sh.jb1 = tid;
-    __syncthreads();
-    const int jb = sh.jb, jb1 = sh.jb1;
-    if (jb != jb1) { k0 = bmax[jb]; k1 = bmin[jb1]; __syncthreads(); return; }
-    const uint32_t nlo = bmin[jb], nhi = bmax[jb];
-    if (nlo >= nhi) { k0 = k1 = nlo; __syncthreads(); return; }
-    // compact the keys of bin jb to the front (rounds of kBlkThreads: writes never pass unread keys)
-    const int below = sh.below, keep = sh.keep;
-    for (int base = 0; base < m; base += kBlkThreads) {
-      const int i = base + tid;
-      const uint32_t k = (i < m) ? buf[i] : 0u;
-      const bool in = (i < m) && (k - nlo) <= (nhi - nlo);
-      __syncthreads();
-      if (in) buf[atomicAdd(&sh.m_next, 1)] = k;
-    }
-    __syncthreads();
-    r -= below;
-    m = keep;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// 5d. boxes: one CTA per box
-// ------------------------------------------------------------------------------------------
-// pass over one sub-rect of the box: MODE 0 = pass 1 (reduce + histogram), MODE 1 = pass 2 (of the keys whose
-// histogram word lies in [tgt, tgt + dt]: count those under klo, append those in [klo, khi] to sortbuf)
+// pass over one sub-rect of the box: MODE 0 = pass 1 (reduce + histogram), MODE 1 = pass 2 (append the keys whose
+// histogram word lies in [tgt, tgt + dt] to sortbuf)
 template <int MODE>
 __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, int W, int rx0, int ry0, int rx1, int ry1,
                                                uint32_t dmax_bits, const FrameTab& tb, float uc, float vc, float s4f, float kkf,
-                                               float ylo, float yhi, uint32_t hist_bias, uint32_t pipe_s, AccQ& acc,
-                                               float& s0_all, float& su, uint32_t tgt, uint32_t dt, uint32_t* sortbuf,
-                                               int* ncoll, uint32_t klo, uint32_t khi, int& below) {
-  constexpr uint32_t kSlot = kBlkThreads * 16;
+                                               float ylo, float yhi, uint32_t hist_bias, AccQ& acc, float& s0_all, float& su,
+                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
   const int tid = threadIdx.x;
   const int rh = ry1 - ry0 + 1;
   const int xa = rx0 & ~3;
@@ -391,24 +200,20 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
     const int rows_l = rh - row_l;
     uint32_t no_cptr = 0u;
     if (MODE == 0) acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kQuadDepth; ++i) {
-      cp_async_16(pipe_s + i * kSlot, gp, (i * RPq < rows_l) ? 16u : 0u);
-      cp_async_commit();
-      gp += rstep;
-    }
-    int nxt_row = kQuadDepth * RPq;
+    // a strip is short (a thread sees a handful of its row steps): the loads of kTileBatch steps are issued together
 #pragma unroll 1
-    for (int st = 0; st < nsteps; st += kQuadDepth) {
+    for (int st = 0; st < nsteps; st += kTileBatch) {
+      uint4 qb[kTileBatch];
 #pragma unroll
-      for (int i = 0; i < kQuadDepth; ++i) {
+      for (int i = 0; i < kTileBatch; ++i) {
+        qb[i] = make_uint4(0u, 0u, 0u, 0u);
+        if ((st + i) * RPq < rows_l) qb[i] = ldg_u4(gp + (size_t)i * rstep);
+      }
+      gp += (size_t)kTileBatch * rstep;
+#pragma unroll
+      for (int i = 0; i < kTileBatch; ++i) {
         if (st + i >= nsteps) break;
-        cp_async_wait<kQuadDepth - 1>();
-        const uint4 q0 = lds_u4(pipe_s + i * kSlot);
-        cp_async_16(pipe_s + i * kSlot, gp, (nxt_row < rows_l) ? 16u : 0u);
-        cp_async_commit();
-        gp += rstep;
-        nxt_row += RPq;
+        const uint4 q0 = qb[i];
         if (MODE == 0) {
           accum_quad_hist<false>(q0, dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, 0u, 0u, no_cptr);
           vr += frp;
@@ -416,21 +221,15 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
           const uint32_t bits[4] = {q0.x, q0.y, q0.z, q0.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (key_valid(bits[j], dm[j])) {
-              const float yc = fminf(fmaxf(fmaf(__uint_as_float(bits[j]), s4f, kkf), 33554432.f), yhi);
-              if ((__float_as_uint(yc) - tgt) <= dt) {
-                if (bits[j] < klo) ++below;
-                else if (bits[j] <= khi) {
-                  const int pos = atomicAdd(ncoll, 1);
-                  if (pos < kTileCollCap) sortbuf[pos] = bits[j];
-                }
-              }
+            const float y = fmaf(__uint_as_float(bits[j]), s4f, kkf);
+            if ((__float_as_uint(y) - tgt) <= dt && key_valid(bits[j], dm[j])) {
+              const int pos = atomicAdd(ncoll, 1);
+              if (pos < kTileCollCap) sortbuf[pos] = bits[j];
             }
           }
         }
       }
     }
-    cp_async_wait<0>();
     if (MODE == 0) {
       const float du = (float)col0 - uc;
       su = fmaf(du, acc.s0[0], fmaf(du + 1.f, acc.s0[1], fmaf(du + 2.f, acc.s0[2], fmaf(du + 3.f, acc.s0[3], su))));
@@ -439,25 +238,72 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
   }
 }
 
-__device__ __forceinline__ uint32_t ldcg_u16(const uint16_t* p) {
-  uint16_t v;
-  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return (uint32_t)v;
+// light pass over the listed tiles (completely inside the rect and the frame: no masks, no geometry).  The 64 quads of
+// a tile go to 64 consecutive threads, so a thread keeps ONE (row, quad column) position and walks the tiles four
+// apart: a load costs one shared-memory read of the tile's offset and one add.  kTileScanBatch loads in flight.
+// MODE 0: histogram update, MODE 1: collect the keys whose histogram word lies in [tgt, tgt + dt].
+#ifndef LM3D_TILE_SCAN_BATCH
+#define LM3D_TILE_SCAN_BATCH 4
+#endif
+constexpr int kTileScanBatch = LM3D_TILE_SCAN_BATCH;
+template <int MODE>
+__device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, int W, const uint32_t* scan_list, int n_scan,
+                                               uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
+                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
+  const float* __restrict__ qp = fbase + (((threadIdx.x & 63) >> 2) * W + (threadIdx.x & 3) * 4);  // (row, quad column) inside a tile
+  constexpr int kLanes = kBlkThreads / kTileQuads;  // tiles in flight per step (4)
+#pragma unroll 1
+  for (int t0 = threadIdx.x >> 6; t0 < n_scan; t0 += kTileScanBatch * kLanes) {
+    uint4 qb[kTileScanBatch];
+#pragma unroll
+    for (int i = 0; i < kTileScanBatch; ++i) {
+      const int t = t0 + i * kLanes;
+      if (t < n_scan) qb[i] = ldg_u4(qp + scan_list[t]);
+    }
+#pragma unroll
+    for (int i = 0; i < kTileScanBatch; ++i) {
+      if (t0 + i * kLanes >= n_scan) break;
+      const uint32_t bits[4] = {qb[i].x, qb[i].y, qb[i].z, qb[i].w};
+      if (MODE == 0) {
+        uint32_t key[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) key[j] = key_valid(bits[j], dmax_bits) ? bits[j] : 0x7fffffffu;
+        float y[4];
+        unpack2(fma2(pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+        unpack2(fma2(pack2(__uint_as_float(key[2]), __uint_as_float(key[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float yc = fminf(fmaxf(y[j], ylo), yhi);  // NaN -> ylo
+          asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias) : "memory");
+        }
+      } else {
+        float y[4];
+        unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+        unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((__float_as_uint(y[j]) - tgt) <= dt && key_valid(bits[j], dmax_bits)) {
+            const int pos = atomicAdd(ncoll, 1);
+            if (pos < kTileCollCap) sortbuf[pos] = bits[j];
+          }
+        }
+      }
+    }
+  }
 }
 
 #ifndef LM3D_TILE_MINB
-#define LM3D_TILE_MINB 3
+#define LM3D_TILE_MINB 2   // 2 x 256 threads at up to 128 registers: measured 2.62 ms vs 3.69 ms (3 CTAs, 80 registers, spills) on C3 x 200
 #endif
 __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
-  uint32_t* hist = smem_u32;                 // [768]: 256 private below | bins 1..254 | 256 private above (| 2 spare)
-  uint32_t* sortbuf = smem_u32 + 768;        // [kTileCollCap]
-  uint32_t* sbin = sortbuf + kTileCollCap;   // [256]: tile prefix sums per bin
+  uint32_t* hist = smem_u32;                           // [256 | kBlkBins | 256] as in lift_block_kernel
+  uint32_t* sortbuf = smem_u32 + kTileHistWords;       // [kSortCap]: lattice sample, then the collected keys
+  uint32_t* scan_list = sortbuf + kSortCap;            // [kTileMaxInt]: pixel offset of the tiles to scan
   __shared__ TileBoxShared sh;
   const LiftArgs& A = T.A;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-  const uint32_t pipe_s = (uint32_t)__cvta_generic_to_shared(sbin + 256) + (uint32_t)tid * 16;
   const int W = A.W, H = A.H;
   const int n_tiles = T.ntx * T.nty;
   const int b_begin = (int)T.frame_off[T.f0], b_end = (int)T.frame_off[T.f0 + T.nf];
@@ -469,56 +315,73 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     const int b = sh.item;
     if (b >= b_end) break;
     const Rect rc = load_rect(A.rect4, b, H, W);
-    if ((long long)rc.w * rc.h <= kSmallMaxPix) continue;   // a warp box: lift_quad_kernel has it
+    const long long n_pix = (long long)rc.w * rc.h;
+    if (n_pix <= kSmallMaxPix) continue;                     // a warp box: lift_quad_kernel has it
     const int f = A.box_frame[b];
+    if (T.frame_area[f] < T.area_thr) continue;              // frame under the cover threshold: lift_block_kernel has it
     const int slot = f - T.f0;
-    const TileMap fm = T.map[slot];
-    if (!fm.tiled) continue;                                 // frame below the cover threshold: lift_block_kernel has it
     const float* __restrict__ fbase = A.depth + (size_t)f * H * W;
     const FrameTab tb = load_tab(A.tab, f);
     const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
 
-    // ---- tiles completely inside the rect (a frame-edge tile is complete when the rect reaches the edge) ----------
-    const int ex1 = (rc.x1 == W - 1) ? T.ntx * kTile - 1 : rc.x1, ey1 = (rc.y1 == H - 1) ? T.nty * kTile - 1 : rc.y1;
-    const int tx_lo = (rc.x0 + kTile - 1) / kTile, tx_hi = (ex1 + 1) / kTile - 1;
-    const int ty_lo = (rc.y0 + kTile - 1) / kTile, ty_hi = (ey1 + 1) / kTile - 1;
-    const bool has_int = tx_lo <= tx_hi && ty_lo <= ty_hi;
+    // ---- sample kTileSample pixels on a lattice, sort, bracket (as lift_block_kernel, half its sample: the sort is
+    //      13 % of this kernel's instructions at 1024; +-3 sigma of 512 = +-6.9 % of the keys, ~25 per histogram bin) ----
+    int svl = 0;
+    for (int i = tid; i < kTileSample; i += kBlkThreads) {
+      const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / kTileSample;
+      const int ry = (int)(idx / rc.w), cx = (int)(idx - (long long)ry * rc.w);
+      const uint32_t bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+      const bool v = key_valid(bits, A.dmax_bits);
+      sortbuf[i] = v ? bits : kKeyInvalid;
+      svl += v;
+    }
+    const int sv = block_sum_i(svl, sh.ls, 0);
+    block_bitonic(sortbuf, kTileSample);
+    uint32_t lo = 1u, hi = kKeyMaxValid;
+    if (sv > 0) {
+      int a, bb;
+      bracket_ranks(sv, A.quant, kBracketZ, a, bb);
+      if (a >= 0) lo = sortbuf[a];
+      if (bb < sv) hi = sortbuf[bb];
+    }
+    hi = min(hi, A.dmax_bits);
+    const float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
+    const float wd = whi_f - wlo_f;
+    const float s4f = (wd > 0.f) ? fminf(4000.f / wd, 2097152.f / whi_f) : 0.f;  // 1000 bins x 4
+    const float kkf = fmaf(-wlo_f, s4f, 33554432.f + 4.f * 268.f);               // window low edge -> word 268
+    const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
+    const uint32_t hist_bias = hist_s - 0x30000000u;
+    __syncthreads();
+    for (int i = tid; i < kTileHistWords; i += kBlkThreads) hist[i] = 0u;
+    if (tid == 0) { sh.n_scan = 0; sh.ncoll = 0; }
+    __syncthreads();
+
+    // ---- tiles completely inside the rect; the rest of the rect = up to four strips -----------------------------
+    const int tx_lo = (rc.x0 + kTile - 1) / kTile, tx_hi = min((rc.x1 + 1) / kTile, T.ntx) - 1;
+    const int ty_lo = (rc.y0 + kTile - 1) / kTile, ty_hi = min((rc.y1 + 1) / kTile, T.nty) - 1;
+    const bool has_int = tx_lo <= tx_hi && ty_lo <= ty_hi && (tx_hi - tx_lo + 1) * (ty_hi - ty_lo + 1) <= kTileMaxInt;
     const int ntx_i = has_int ? tx_hi - tx_lo + 1 : 0, nty_i = has_int ? ty_hi - ty_lo + 1 : 0;
     const int n_int = ntx_i * nty_i;
-    // boundary strips: top, bottom (full width), left, right (interior rows); without interior tiles the whole rect
     int sr[4][4];
     int n_sr = 0;
     if (!has_int) {
       sr[0][0] = rc.x0; sr[0][1] = rc.y0; sr[0][2] = rc.x1; sr[0][3] = rc.y1; n_sr = 1;
     } else {
-      const int iy0 = ty_lo * kTile, iy1 = min((ty_hi + 1) * kTile - 1, rc.y1);
-      const int ix0 = tx_lo * kTile, ix1 = min((tx_hi + 1) * kTile - 1, rc.x1);
+      const int iy0 = ty_lo * kTile, iy1 = (ty_hi + 1) * kTile - 1;
+      const int ix0 = tx_lo * kTile, ix1 = (tx_hi + 1) * kTile - 1;
       if (rc.y0 < iy0) { sr[n_sr][0] = rc.x0; sr[n_sr][1] = rc.y0; sr[n_sr][2] = rc.x1; sr[n_sr][3] = iy0 - 1; ++n_sr; }
       if (iy1 < rc.y1) { sr[n_sr][0] = rc.x0; sr[n_sr][1] = iy1 + 1; sr[n_sr][2] = rc.x1; sr[n_sr][3] = rc.y1; ++n_sr; }
       if (rc.x0 < ix0) { sr[n_sr][0] = rc.x0; sr[n_sr][1] = iy0; sr[n_sr][2] = ix0 - 1; sr[n_sr][3] = iy1; ++n_sr; }
       if (ix1 < rc.x1) { sr[n_sr][0] = ix1 + 1; sr[n_sr][1] = iy0; sr[n_sr][2] = rc.x1; sr[n_sr][3] = iy1; ++n_sr; }
     }
 
-    for (int i = tid; i < 768; i += kBlkThreads) hist[i] = 0u;
-    __syncthreads();
-    const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(kTileWordAbove + tid);
-    const uint32_t hist_bias = hist_s - 0x30000000u;
-
-    // ---- pass 1 over the strips ---------------------------------------------------------------------------
+    // ---- interior tiles: summaries; the tiles whose depth range straddles the bracket go on the scan list ----------
     AccQ acc;
     acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
     acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
     acc.sv = 0.f; acc.n_valid = 0.f;
-    float s0_all = 0.f, su = 0.f;
-    int nv_dummy = 0;
-    for (int s = 0; s < n_sr; ++s)
-      tile_rect_pass<0>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, fm.s4f, fm.kkf, ylo, yhi,
-                        hist_bias, pipe_s, acc, s0_all, su, 0u, 0u, nullptr, nullptr, 0u, 0u, nv_dummy);
-
-    // ---- interior tiles: summaries (a thread per tile) and per-bin prefix sums (a thread per bin) ------------------
-    double ds0 = (double)s0_all, dsu = (double)su, dsv = (double)acc.sv;
-    int nv_t = (int)acc.n_valid;
-    uint32_t sb = 0u;
+    double ds0 = 0.0, dsu = 0.0, dsv = 0.0;
+    int nv_t = 0, below_t = 0, nvs_t = 0;
     if (has_int) {
       const TileSum* ts = T.tsum + (size_t)slot * n_tiles;
       for (int i = tid; i < n_int; i += kBlkThreads) {
@@ -527,47 +390,50 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
         const float4* p = reinterpret_cast<const float4*>(ts + (ty * T.ntx + tx));
         const float4 a = __ldcg(p), m = __ldcg(p + 1), x = __ldcg(p + 2);
         const int nv = __float_as_int(a.x);
-        nv_t += nv;
-        const double s0 = (double)a.y;
-        ds0 += s0;
-        dsu += (double)a.z + ((double)(tx * kTile) + 15.5 - (double)uc) * s0;
-        dsv += (double)a.w + ((double)(ty * kTile) + 15.5 - (double)vc) * s0;
-        acc.mn0 = fminf(acc.mn0, m.x); acc.mn1 = fminf(acc.mn1, m.y); acc.mn2 = fminf(acc.mn2, m.z);
-        acc.mx0 = fmaxf(acc.mx0, m.w); acc.mx1 = fmaxf(acc.mx1, x.x); acc.mx2 = fmaxf(acc.mx2, x.y);
-      }
-      const uint16_t* cdf = T.tcdf + (size_t)slot * n_tiles * kTileBins + tid;
-      for (int iy = 0; iy < nty_i; ++iy) {
-        const uint16_t* rowp = cdf + (size_t)((ty_lo + iy) * T.ntx + tx_lo) * kTileBins;
-        int ix = 0;
-        for (; ix + 4 <= ntx_i; ix += 4) {
-          const uint32_t v0 = ldcg_u16(rowp + (size_t)(ix + 0) * kTileBins), v1 = ldcg_u16(rowp + (size_t)(ix + 1) * kTileBins);
-          const uint32_t v2 = ldcg_u16(rowp + (size_t)(ix + 2) * kTileBins), v3 = ldcg_u16(rowp + (size_t)(ix + 3) * kTileBins);
-          sb += (v0 + v1) + (v2 + v3);
+        if (nv > 0) {
+          nv_t += nv;
+          const double s0 = (double)a.y;
+          ds0 += s0;
+          dsu += (double)a.z + ((double)(tx * kTile) + 7.5 - (double)uc) * s0;
+          dsv += (double)a.w + ((double)(ty * kTile) + 7.5 - (double)vc) * s0;
+          acc.mn0 = fminf(acc.mn0, m.x); acc.mn1 = fminf(acc.mn1, m.y); acc.mn2 = fminf(acc.mn2, m.z);
+          acc.mx0 = fmaxf(acc.mx0, m.w); acc.mx1 = fmaxf(acc.mx1, x.x); acc.mx2 = fmaxf(acc.mx2, x.y);
+          // depth range vs the bracket [lo, hi] (keys): all under -> counted, all over -> nothing, else scanned
+          if (__float_as_uint(x.w) < lo) below_t += nv;
+          else if (__float_as_uint(x.z) <= hi) { scan_list[atomicAdd(&sh.n_scan, 1)] = (uint32_t)((ty * kTile) * W + tx * kTile); nvs_t += nv; }
         }
-        for (; ix < ntx_i; ++ix) sb += ldcg_u16(rowp + (size_t)ix * kTileBins);
       }
     }
-    sbin[tid] = sb;
+
+    // ---- pass 1: strips pixel by pixel, listed tiles with the light pass -----------------------------------------
+    float s0_all = 0.f, su = 0.f;
+    for (int s = 0; s < n_sr; ++s)
+      tile_rect_pass<0>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
+                        acc, s0_all, su, 0u, 0u, nullptr, nullptr);
+    const int nv_strips_l = (int)acc.n_valid;
+    __syncthreads();
+    const int n_scan = sh.n_scan;
+    tile_scan_pass<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr);
 
     // ---- block reduction -----------------------------------------------------------------------------------
     {
-      const double d0 = warp_sum_d(ds0), d1 = warp_sum_d(dsu), d2 = warp_sum_d(dsv);
+      const double d0 = warp_sum_d(ds0 + (double)s0_all), d1 = warp_sum_d(dsu + (double)su), d2 = warp_sum_d(dsv + (double)acc.sv);
       const float f0 = warp_min_f(acc.mn0), f1 = warp_min_f(acc.mn1), f2 = warp_min_f(acc.mn2);
       const float f3 = warp_max_f(acc.mx0), f4 = warp_max_f(acc.mx1), f5 = warp_max_f(acc.mx2);
-      const int i0 = warp_sum_i(nv_t), i1 = warp_sum_i((int)acc.n_valid);
+      const int i0 = warp_sum_i(nv_t + nv_strips_l), i1 = warp_sum_i(nv_strips_l), i2 = warp_sum_i(below_t), i3 = warp_sum_i(nvs_t);
       __syncthreads();
       if (lane == 0) {
         sh.red_d[warp][0] = d0; sh.red_d[warp][1] = d1; sh.red_d[warp][2] = d2;
         sh.red_f[warp][0] = f0; sh.red_f[warp][1] = f1; sh.red_f[warp][2] = f2;
         sh.red_f[warp][3] = f3; sh.red_f[warp][4] = f4; sh.red_f[warp][5] = f5;
-        sh.red_i[warp][0] = i0; sh.red_i[warp][1] = i1;
+        sh.red_i[warp][0] = i0; sh.red_i[warp][1] = i1; sh.red_i[warp][2] = i2; sh.red_i[warp][3] = i3;
       }
       __syncthreads();
     }
     BoxSums S;
     S.s0 = S.su = S.sv = 0.0;
     S.n_valid = 0;
-    int nv_strips = 0;
+    int nv_strips = 0, below_tiles = 0, nv_scanned = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { S.mn[k] = INFINITY; S.mx[k] = -INFINITY; }
     for (int w = 0; w < kBlkWarps; ++w) {
@@ -579,23 +445,22 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       }
       S.n_valid += sh.red_i[w][0];
       nv_strips += sh.red_i[w][1];
+      below_tiles += sh.red_i[w][2];
+      nv_scanned += sh.red_i[w][3];
     }
 
-    // ---- combined histogram: thread t owns bin t -------------------------------------------------------------
+    // ---- which bins hold the target ranks?  thread t owns bin words 256 + 4 t .. + 3 ------------------------------
     int r = 0; bool two = false; double gamma = 0.0;
     if (S.n_valid > 0) order_ranks(S.n_valid, A.quant, r, two, gamma);
     const int r1 = r + (two ? 1 : 0);
     uint32_t k0 = 0, k1 = 0;
-    bool fallback = false;
+    bool handover = false;
     if (S.n_valid > 0) {
-      const int below_all = block_sum_i((int)hist[tid], sh.ls, 0), above = block_sum_i((int)hist[kTileWordAbove + tid], sh.ls, 1);
-      int in_l = 0;
-      if (tid >= 1 && tid <= kTileBins - 2) in_l = (int)hist[kTileWordBin1 + tid - 1];
-      const int in_all = block_sum_i(in_l, sh.ls, 2);
-      int cnt = in_l + (int)(sbin[tid] - (tid > 0 ? sbin[tid - 1] : 0u));
-      if (tid == 0) cnt += below_all - (below_all + in_all + above - nv_strips);
-      if (tid == kTileBins - 1) cnt += above;
-      int incl = cnt;
+      const int below_all = block_sum_i((int)hist[tid], sh.ls, 0), above = block_sum_i((int)hist[256 + kBlkBins + tid], sh.ls, 1);
+      const uint4 h4 = reinterpret_cast<const uint4*>(hist + 256)[tid];
+      const int c4[4] = {(int)h4.x, (int)h4.y, (int)h4.z, (int)h4.w};
+      const int c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+      int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(kFull, incl, o);
@@ -603,129 +468,56 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       }
       __syncthreads();
       if (lane == 31) sh.scan_w[warp] = incl;
-      if (tid == 0) { sh.b_lo = -1; sh.b_hi = -1; sh.before = 0; sh.end = 0; sh.ncoll = 0; }
+      if (tid == 0) { sh.b_lo = -1; sh.b_hi = -1; sh.before = 0; sh.end = 0; }
       __syncthreads();
-      int wpre = 0;
+      int wpre = 0, in_all = 0;
 #pragma unroll
-      for (int w = 0; w < kBlkWarps; ++w) if (w < warp) wpre += sh.scan_w[w];
-      const int cum = wpre + incl - cnt;
-      if (r >= cum && r < cum + cnt) { sh.b_lo = tid; sh.before = cum; }
-      if (r1 >= cum && r1 < cum + cnt) { sh.b_hi = tid; sh.end = cum + cnt; }
+      for (int w = 0; w < kBlkWarps; ++w) { if (w < warp) wpre += sh.scan_w[w]; in_all += sh.scan_w[w]; }
+      // Every histogram update is one slot; the slots that were not valid pixels (masked strip lanes, invalid pixels
+      // of strips and scanned tiles) all sit in the private "below" words.  Valid keys that went through the
+      // histogram = strips + scanned tiles (their counts are known), so the valid keys under the bracket are
+      // below_all - (slots - valid), plus the tiles that were counted as "all under" without a scan.
+      const int slots = below_all + in_all + above;
+      const int below = below_tiles + below_all - (slots - nv_strips - nv_scanned);
+      int cum = below + wpre + incl - c;  // valid keys before this thread's bins
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r >= cum && r < cum + c4[i]) { sh.b_lo = 256 + 4 * tid + i; sh.before = cum; }
+        if (r1 >= cum && r1 < cum + c4[i]) { sh.b_hi = 256 + 4 * tid + i; sh.end = cum + c4[i]; }
+        cum += c4[i];
+      }
       __syncthreads();
       const int b_lo = sh.b_lo, b_hi = sh.b_hi, before = sh.before;
       const int n_coll = sh.end - before;
-      if (b_lo < 1 || b_hi > kTileBins - 2 || b_hi < b_lo) {
-        fallback = true;  // a target rank sits in a catch-all bin
-        if (tid == 0) atomicAdd(&A.counters[16], 1);
+      if (b_lo < 256 || b_hi < b_lo || n_coll > kTileCollCap) {
+        // the bracket missed the rank (3 sigma of the sample: a few boxes per thousand), or ties overfill the target
+        // bins: lift_block_kernel refines.  (A retry loop around this body was measured: the live ranges it adds
+        // cost 35 % of the kernel -- 128 registers and spills -- to save the 0.5 ms tail of a few handed-over boxes.)
+        handover = true;
       } else {
-        const uint16_t* cdf = T.tcdf + (size_t)slot * n_tiles * kTileBins;
-        const uint32_t* srt = T.tsorted + (size_t)slot * n_tiles * kTilePix;
-        uint32_t klo = 0u, khi = 0xffffffffu;  // key window inside the target bins (level 2)
-        const bool lvl2 = n_coll > kTileCollCap;
-        if (lvl2) {
-          // ---- LEVEL 2: the target bins hold more keys than fit (a flat surface: tens of thousands of pixels within a
-          //      few millimetres).  A systematic sample of the interior tiles' runs brackets the rank in KEY space;
-          //      one streaming pass then counts the keys under the bracket and collects the few per cent inside it.
-          //      The strips' share of the bins is not sampled: the bracket is widened by it on the low side. -----------
-          const int n_strip_b = block_sum_i((tid >= b_lo && tid <= b_hi) ? in_l : 0, sh.ls, 3);
-          const int n_runs_b = n_coll - n_strip_b;
-          if (n_runs_b < 64 || n_int >= kTileSampleCap / 2) {
-            fallback = true;
-            if (tid == 0) atomicAdd(&A.counters[17], 1);
-          } else {
-            const int stride = (n_runs_b + (kTileSampleCap - n_int) - 1) / (kTileSampleCap - n_int);
-            for (int i = tid; i < n_int; i += kBlkThreads) {
-              const int iy = i / ntx_i, ix = i - iy * ntx_i;
-              const size_t tile = (size_t)(ty_lo + iy) * T.ntx + tx_lo + ix;
-              const int s = (int)ldcg_u16(cdf + tile * kTileBins + b_lo - 1), e = (int)ldcg_u16(cdf + tile * kTileBins + b_hi);
-              const uint32_t* src = srt + tile * kTilePix;
-              for (int k = s + (stride >> 1); k < e; k += stride) {
-                const uint32_t v = __ldcg(src + k);
-                const int pos = atomicAdd(&sh.ncoll, 1);
-                if (pos < kTileSampleCap) { sortbuf[pos] = v; sortbuf[kTileSampleCap + pos] = v; }
-              }
-            }
-            __syncthreads();
-            const int m = min(sh.ncoll, kTileSampleCap);
-            __syncthreads();
-            if (tid == 0) sh.ncoll = 0;
-            const int rr0 = r - before;
-            const float q_lo = (float)max(0, rr0 - n_strip_b) / (float)n_runs_b, q_hi = fminf((float)(rr0 + 1) / (float)n_runs_b, 1.f);
-            const float fm_ = (float)m;
-            const int a = (int)floorf(q_lo * fm_ - (3.f * sqrtf(fm_ * q_lo * (1.f - q_lo)) + 2.f));
-            const int bq = (int)ceilf(q_hi * fm_ + (3.f * sqrtf(fm_ * q_hi * (1.f - q_hi)) + 2.f));
-            uint32_t tmp;
-            if (a >= 0) block_select_smem(sortbuf, m, min(a, m - 1), false, hist, sh, klo, tmp);
-            if (bq < m) block_select_smem(sortbuf + kTileSampleCap, m, bq, false, hist, sh, khi, tmp);
-            __syncthreads();
-          }
-        }
-        if (!fallback) {
-          // ---- the keys of bins b_lo .. b_hi (inside [klo, khi]): bin-sorted runs of the interior tiles + a second
-          //      pass over the strips ---------------------------------------------------------------------------
-          int below_l = 0;
-          if (has_int && !lvl2) {
-            for (int i = tid; i < n_int; i += kBlkThreads) {   // short runs: a thread per tile
-              const int iy = i / ntx_i, ix = i - iy * ntx_i;
-              const size_t tile = (size_t)(ty_lo + iy) * T.ntx + tx_lo + ix;
-              const int s = (int)ldcg_u16(cdf + tile * kTileBins + b_lo - 1), e = (int)ldcg_u16(cdf + tile * kTileBins + b_hi);
-              if (e > s) {
-                int pos = atomicAdd(&sh.ncoll, e - s);
-                const uint32_t* src = srt + tile * kTilePix;
-                int k = s;
-                for (; k + 4 <= e; k += 4, pos += 4) {
-                  const uint32_t v0 = __ldcg(src + k), v1 = __ldcg(src + k + 1), v2 = __ldcg(src + k + 2), v3 = __ldcg(src + k + 3);
-                  if (pos + 3 < kTileCollCap) { sortbuf[pos] = v0; sortbuf[pos + 1] = v1; sortbuf[pos + 2] = v2; sortbuf[pos + 3] = v3; }
-                }
-                for (; k < e; ++k, ++pos)
-                  if (pos < kTileCollCap) sortbuf[pos] = __ldcg(src + k);
-              }
-            }
-          } else if (has_int) {
-            for (int i = warp; i < n_int; i += kBlkWarps) {     // long runs: a warp per tile, four loads in flight per lane
-              const int iy = i / ntx_i, ix = i - iy * ntx_i;
-              const size_t tile = (size_t)(ty_lo + iy) * T.ntx + tx_lo + ix;
-              const int s = (int)ldcg_u16(cdf + tile * kTileBins + b_lo - 1), e = (int)ldcg_u16(cdf + tile * kTileBins + b_hi);
-              const uint32_t* src = srt + tile * kTilePix;
-              for (int kb = s + lane; kb < e; kb += 128) {
-                uint32_t v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = (kb + 32 * u < e) ? __ldcg(src + kb + 32 * u) : 0u;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (kb + 32 * u < e) {
-                    if (v[u] < klo) ++below_l;
-                    else if (v[u] <= khi) {
-                      const int pos = atomicAdd(&sh.ncoll, 1);
-                      if (pos < kTileCollCap) sortbuf[pos] = v[u];
-                    }
-                  }
-                }
-              }
-            }
-          }
-          const uint32_t tgt = 0x4C000000u + (uint32_t)(kTileWordBin1 + b_lo - 1), dt = (uint32_t)(b_hi - b_lo);
-          float dummy0 = 0.f, dummy1 = 0.f;
-          for (int s = 0; s < n_sr; ++s)
-            tile_rect_pass<1>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, fm.s4f, fm.kkf, ylo, yhi,
-                              hist_bias, pipe_s, acc, dummy0, dummy1, tgt, dt, sortbuf, &sh.ncoll, klo, khi, below_l);
-          const int below2 = lvl2 ? block_sum_i(below_l, sh.ls, 0) : 0;
+        const uint32_t tgt = 0x4C000000u + (uint32_t)b_lo, dt = (uint32_t)(b_hi - b_lo);
+        float d0 = 0.f, d1 = 0.f;
+        for (int s = 0; s < n_sr; ++s)
+          tile_rect_pass<1>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
+                            acc, d0, d1, tgt, dt, sortbuf, &sh.ncoll);
+        tile_scan_pass<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll);
+        __syncthreads();
+        if (sh.ncoll != n_coll) {
+          handover = true;  // (cannot happen: both passes evaluate the same map)
+          if (tid == 0) atomicAdd(&A.counters[15], 1);
+        } else {
+          int np2 = 32;
+          while (np2 < n_coll) np2 <<= 1;
+          for (int i = n_coll + tid; i < np2; i += kBlkThreads) sortbuf[i] = kKeyInvalid;
+          block_bitonic(sortbuf, np2);
+          const int rl = r - before;
+          k0 = sortbuf[rl];
+          k1 = two ? sortbuf[rl + 1] : k0;
           __syncthreads();
-          const int ncoll = sh.ncoll, rr = r - before - below2;
-          if (!lvl2 && ncoll != n_coll) {
-            fallback = true;  // (cannot happen: both passes evaluate the same map)
-            if (tid == 0) atomicAdd(&A.counters[15], 1);
-          } else if (ncoll > kTileCollCap || rr < 0 || rr + (two ? 1 : 0) >= ncoll) {
-            fallback = true;  // level 2: the bracket missed the rank or holds too many keys (ties)
-            if (tid == 0) atomicAdd(&A.counters[ncoll > kTileCollCap ? 18 : 19], 1);
-          } else {
-            if (lvl2 && tid == 0) atomicAdd(&A.counters[13], 1);
-            block_select_smem(sortbuf, ncoll, rr, two, hist, sh, k0, k1);
-          }
         }
       }
     }
-    if (fallback) {
+    if (handover) {
       if (tid == 0) {
         const int pos = atomicAdd(&A.counters[1], 1);
         const_cast<int32_t*>(A.list)[pos] = b;
@@ -733,9 +525,11 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       }
       continue;
     }
-    if (tid == 0)
+    if (tid == 0) {
       write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr, tb,
                    rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
+      push_record(A, b);
+    }
   }
 }
 

@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) lift_tma_kernel(const __gri
       write_record_f32(reinterpret_cast<float*>(A.out + cur.b), A.order_stats ? A.order_stats + 2 * (size_t)cur.b : nullptr,
                        tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
                        (float)(1.0 / A.scale_depth));
+      push_record(A, cur.b);
     }
     __syncwarp();
 

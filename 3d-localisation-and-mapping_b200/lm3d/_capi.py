@@ -23,6 +23,11 @@ SYMBOLS = (
     "lm3d_lift_workspace_bytes",
     "lm3d_scale_boxes",
     "lm3d_lift_boxes",
+    "lm3d_lift_boxes_gather",
+    "lm3d_gather_alloc",
+    "lm3d_gather_open",
+    "lm3d_gather_close",
+    "lm3d_gather_free",
     "lm3d_cloud_workspace_bytes",
     "lm3d_lift_frame_cloud",
     "lm3d_ingest_depth",
@@ -75,6 +80,16 @@ def load():
     lib.lm3d_scale_boxes.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, vp]
     lib.lm3d_lift_boxes.restype = C.c_int
     lib.lm3d_lift_boxes.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp, sz, vp]
+    lib.lm3d_lift_boxes_gather.restype = C.c_int
+    lib.lm3d_lift_boxes_gather.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp, sz, vp, i32, i64, vp]
+    lib.lm3d_gather_alloc.restype = C.c_int
+    lib.lm3d_gather_alloc.argtypes = [sz, C.POINTER(vp), vp]
+    lib.lm3d_gather_open.restype = C.c_int
+    lib.lm3d_gather_open.argtypes = [vp, C.POINTER(vp)]
+    lib.lm3d_gather_close.restype = C.c_int
+    lib.lm3d_gather_close.argtypes = [vp]
+    lib.lm3d_gather_free.restype = C.c_int
+    lib.lm3d_gather_free.argtypes = [vp]
     lib.lm3d_lift_frame_cloud.restype = C.c_int
     lib.lm3d_lift_frame_cloud.argtypes = [vp, i64, i32, i32, vp, vp, dbl, dbl, vp, vp, vp, sz, vp]
     lib.lm3d_cloud_workspace_bytes.restype = sz

@@ -58,6 +58,88 @@ def gather_counts(n_local: int, device, group=None) -> list[int]:
     return [int(v) for v in out.cpu()]
 
 
+class _DevBuffer:
+    """A raw device allocation exposed through ``__cuda_array_interface__`` so torch can view it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+
+class PeerGather:
+    """Record gather FUSED into the lift (``lm3d_lift_boxes_gather``): no collective call.
+
+    Every rank owns ``slots`` gather buffers of ``world * n_records`` records (``cudaMalloc`` + CUDA IPC handle,
+    exchanged once through the process group); each rank maps all its peers' buffers (NVLink peer access) and hands
+    the lift a table of ``world`` pointers per slot.  The lift kernels then store every finished record to all of
+    them at ``rank * n_records + b`` -- the all-gather happens as a side effect of the kernel epilogues, spread over
+    the kernel's duration, without a communication kernel competing for the SMs of a persistent grid (what limited
+    the NCCL path: ``PipelinedGather`` below, kept as the baseline and as the parity reference).
+
+    The stores of a call are complete when its stream reaches the end of the call on every rank: ``barrier()``
+    (stream sync + process-group barrier) before reading ``buffer(slot)``.  Equal ``n_records`` on every rank."""
+
+    def __init__(self, n_records: int, device, slots: int = 2, group=None):
+        import ctypes as C
+
+        from . import _capi
+
+        self.lib = _capi.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_records = int(n_records)
+        self.device = torch.device(device)
+        self.slots = int(slots)
+        nbytes = self.world * self.n_records * 96
+        self._own, self._opened, handles = [], [], []
+        with torch.cuda.device(self.device):
+            for _ in range(self.slots):
+                ptr = C.c_void_p()
+                h = C.create_string_buffer(64)
+                _capi.check(self.lib.lm3d_gather_alloc(nbytes, C.byref(ptr), h), "lm3d_gather_alloc")
+                self._own.append(ptr.value)
+                handles.append(h.raw)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handles, group=group)
+            self.tables = []  # per slot: ctypes array of `world` device pointers (index = destination rank)
+            for s in range(self.slots):
+                tab = (C.c_void_p * self.world)()
+                for r in range(self.world):
+                    if r == self.rank:
+                        tab[r] = self._own[s]
+                    else:
+                        ptr = C.c_void_p()
+                        _capi.check(self.lib.lm3d_gather_open(everyone[r][s], C.byref(ptr)), "lm3d_gather_open")
+                        self._opened.append(ptr.value)
+                        tab[r] = ptr.value
+                self.tables.append(tab)
+        self._views = [torch.as_tensor(_DevBuffer(p, nbytes), device=self.device).view(torch.float32).view(self.world * self.n_records, 24)
+                       for p in self._own]
+
+    @property
+    def box_offset(self) -> int:
+        return self.rank * self.n_records
+
+    def buffer(self, slot: int) -> torch.Tensor:
+        """This rank's gathered ``[world * n_records, 24]`` float32 view of ``slot`` (valid after ``barrier()``)."""
+        return self._views[slot]
+
+    def barrier(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            self.barrier()
+            for p in self._opened:
+                self.lib.lm3d_gather_close(p)
+            self.barrier()
+            for p in self._own:
+                self.lib.lm3d_gather_free(p)
+        self._opened, self._own, self._views = [], [], []
+
+
 class PipelinedGather:
     """Overlap the record all-gather of step ``i`` with the lift of step ``i+1``.
 

@@ -105,8 +105,12 @@ def lift_boxes(
     q: float = 50.0,
     plan: LiftPlan | None = None,
     order_stats: bool = False,
+    gather=None,
+    gather_slot: int = 0,
 ):
-    """Lift every box of a sequence (``lm3d_lift_boxes``).
+    """Lift every box of a sequence (``lm3d_lift_boxes``; with ``gather`` -- an ``lm3d.dist.PeerGather`` -- the
+    multi-GPU entry ``lm3d_lift_boxes_gather``, which also stores every record into slot ``gather_slot`` of every
+    rank's gather buffer).
 
     depth ``[F,H,W]`` f32 mm, pose7 ``[F,7]`` f64, intr4 ``[F,4]`` f64 (depth resolution),
     rect4 ``[B,4]`` i32, frame_off ``[F+1]`` i64 -- all CUDA, contiguous.  Returns the
@@ -132,11 +136,21 @@ def lift_boxes(
         raise ValueError("LiftPlan too small for this call")
     os_ptr = plan.order_stats.data_ptr() if plan.order_stats is not None else None
     with torch.cuda.device(depth.device):
-        st = lib.lm3d_lift_boxes(
-            depth.data_ptr(), F, H, W, pose7.data_ptr(), intr4.data_ptr(), rect4.data_ptr(), frame_off.data_ptr(), B,
-            float(scale_depth), float(max_depth_mm), float(q), plan.records.data_ptr(), os_ptr,
-            plan.workspace.data_ptr(), plan.workspace.numel(), _stream_ptr(depth.device),
-        )
+        if gather is None:
+            st = lib.lm3d_lift_boxes(
+                depth.data_ptr(), F, H, W, pose7.data_ptr(), intr4.data_ptr(), rect4.data_ptr(), frame_off.data_ptr(), B,
+                float(scale_depth), float(max_depth_mm), float(q), plan.records.data_ptr(), os_ptr,
+                plan.workspace.data_ptr(), plan.workspace.numel(), _stream_ptr(depth.device),
+            )
+        else:
+            if B > gather.n_records:
+                raise ValueError("more boxes than the gather buffers hold per rank")
+            st = lib.lm3d_lift_boxes_gather(
+                depth.data_ptr(), F, H, W, pose7.data_ptr(), intr4.data_ptr(), rect4.data_ptr(), frame_off.data_ptr(), B,
+                float(scale_depth), float(max_depth_mm), float(q), plan.records.data_ptr(), os_ptr,
+                plan.workspace.data_ptr(), plan.workspace.numel(), gather.tables[gather_slot], gather.world,
+                gather.box_offset, _stream_ptr(depth.device),
+            )
     _capi.check(st, "lm3d_lift_boxes")
     rec = plan.records[:B]
     if plan.order_stats is not None:

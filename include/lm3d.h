@@ -59,9 +59,8 @@ int lm3d_version(void);
 const char* lm3d_status_string(int status);
 
 /* Scratch the lift needs for F frames / B boxes (frame table, box->frame map, work lists): the minimum
- * lm3d_lift_boxes accepts.  lm3d_lift_workspace_bytes adds, for frames of H x W, the scratch of the tile-pyramid
- * path (large frames whose boxes overlap heavily: per-tile summaries, histograms and bin-sorted keys for a chunk
- * of frames); lm3d_lift_boxes uses whatever the workspace holds beyond the minimum, and falls back to one CTA per
+ * lm3d_lift_boxes accepts.  lm3d_lift_workspace_bytes adds, for frames of H x W, the scratch of the tile path
+ * (large frames whose boxes overlap heavily: 64-byte summaries of every 16 x 16 tile for a chunk of frames); lm3d_lift_boxes uses whatever the workspace holds beyond the minimum, and falls back to one CTA per
  * box when it holds less than one frame's worth. */
 size_t lm3d_workspace_bytes(int64_t F, int64_t B);
 size_t lm3d_lift_workspace_bytes(int64_t F, int32_t H, int32_t W, int64_t B);
@@ -94,6 +93,25 @@ int lm3d_lift_boxes(const float* depth, int64_t F, int32_t H, int32_t W, const d
                     const double* intr4, const int32_t* rect4, const int64_t* frame_off, int64_t B,
                     double scale_depth, double max_depth_mm, double q_percent, lm3d_box_out* out,
                     float* order_stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Multi-GPU: the lift with the record gather FUSED into its epilogue (frames shard across ranks, the
+ * only exchange is the per-box records).  Same as lm3d_lift_boxes, and every finished record b is also stored to
+ * peer_out[p][box_offset + b] for p < n_peers (<= 8): device pointers valid on THIS device -- this rank's own gather
+ * buffer and the peers' buffers mapped over NVLink (lm3d_gather_open).  peer_out itself is a HOST array.  The stores
+ * ride along with the kernels (no collective call, no extra kernel, no SM given up to a communication library);
+ * they are complete when the stream reaches the end of the call -- a cross-rank barrier after that (the one the
+ * caller needs anyway before reading its buffer) is all the synchronisation there is.
+ * lm3d_gather_alloc: cudaMalloc'd buffer + its 64-byte CUDA IPC handle; lm3d_gather_open maps another process's
+ * buffer from its handle (lazy peer access); _close / _free undo them. */
+int lm3d_lift_boxes_gather(const float* depth, int64_t F, int32_t H, int32_t W, const double* pose7,
+                           const double* intr4, const int32_t* rect4, const int64_t* frame_off, int64_t B,
+                           double scale_depth, double max_depth_mm, double q_percent, lm3d_box_out* out,
+                           float* order_stats, void* workspace, size_t workspace_bytes, void* const* peer_out,
+                           int32_t n_peers, int64_t box_offset, void* stream);
+int lm3d_gather_alloc(size_t bytes, void** dev_ptr, void* ipc_handle64);
+int lm3d_gather_open(const void* ipc_handle64, void** dev_ptr);
+int lm3d_gather_close(void* dev_ptr);
+int lm3d_gather_free(void* dev_ptr);
 
 /* Full-frame world point cloud: replaces Visualiser.gen_rgbd + gen_point_cloud
  * (pose_processor.py:154-156, 262-271; Open3D unprojection + extrinsic) for F frames.
@@ -153,7 +171,7 @@ int64_t lm3d_kernel_launches(void);
  * [0] frame table (prep_frames_kernel), [1] box prep (prep_boxes_kernel, tile_route_kernel),
  * [2] warp-per-box lift fed by TMA tiles (lift_tma_kernel; only with LM3D_WARP_PATH=tma),
  * [3] warp-per-box lift (lift_quad_kernel + lift_resolve_kernel; lift_hist_kernel when W % 4 != 0),
- * [4] tile-pyramid path (tile_map / tile_build / tile_box kernels of every frame chunk),
+ * [4] tile path (tile_sum_kernel + tile_box_kernel of every frame chunk),
  * [5] CTA-per-box lift (lift_block_kernel). */
 int lm3d_profile_enable(int on);
 int lm3d_profile_read(float* ms6);

@@ -91,9 +91,10 @@ def test_block_kernel_refinement_and_bisection_paths_are_reached(cuda_device, mo
     depth = (1000 + 50 * rng.random((3, H, W))).astype(np.float32)
     rect = (0, 0, W - 1, H - 1)
     lat = _lattice_mask(H * W, 1024).reshape(H, W)
-    depth[0][lat] = 30000.0     # bracket lands at 30 m: the rank is far below it -> refine twice -> bisection
-    depth[1][lat] = 1.0         # bracket lands at 1 mm: the rank is far above it
-    depth[2][lat] = 1030.0      # a mild miss: one refinement pass catches it
+    n_lat = int(lat.sum())
+    depth[0][lat] = (30000.0 + 100.0 * rng.random(n_lat)).astype(np.float32)  # bracket at 30 m: the rank is far below -> two refinements miss -> bisection
+    depth[1][lat] = (1.0 + rng.random(n_lat)).astype(np.float32)             # bracket at 1 mm: the rank is far above it
+    depth[2][lat] = (1052.0 + rng.random(n_lat)).astype(np.float32)          # a mild miss: one refinement pass catches it
     rects = [rect, (3, 5, W - 2, H - 7)] * 3
     frame_off = np.array([0, 2, 4, 6], dtype=np.int64)
     for q in (50.0, 20.0):

@@ -1,6 +1,6 @@
-"""GPU parity of the tile-pyramid path (csrc/lm3d_lift_tiles.cuh): large frames read once in 32x32 tiles, boxes
-take the summaries / histograms / bin-sorted keys of the tiles they cover completely and walk only their boundary
-strips pixel by pixel.  Everything goes through the C ABI and is compared with the numpy oracle; the order
+"""GPU parity of the tile path (csrc/lm3d_lift_tiles.cuh): large frames summarised once in 16x16 tiles; a box takes
+the sums / extents / counts of the tiles it covers completely, scans only the tiles whose depth range straddles its
+percentile bracket, and walks its boundary strips pixel by pixel.  Everything goes through the C ABI and is compared with the numpy oracle; the order
 statistics must be bit-exact, and the path must really have been taken (workspace counters)."""
 import numpy as np
 import pytest
