@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "lm3d.h"
+
 namespace lm3d {
 
 constexpr uint32_t kFull = 0xffffffffu;
@@ -383,11 +385,14 @@ __device__ __forceinline__ void write_record_depth_f32(float* __restrict__ outw,
   if (ostats) { ostats[0] = dlo; ostats[1] = dhi; }
 }
 
+// peers / n_peer / peer_idx: the fused record gather (lm3d_lift_boxes_gather) -- the record is also stored, straight
+// from the registers it was assembled in, to record index peer_idx of every peer buffer.
 __device__ __forceinline__ void write_record_f32(float* __restrict__ outw, float* __restrict__ ostats,
                                                  const FrameTab& tb, int x0, int y0, int x1, int y1, float uc,
                                                  float vc, float s0, float su, float sv, const float (&mn)[3],
                                                  const float (&mx)[3], int n_valid, uint32_t k0, uint32_t k1,
-                                                 float gamma, float inv_scale) {
+                                                 float gamma, float inv_scale, lm3d_box_out* const* peers = nullptr,
+                                                 int n_peer = 0, long long peer_idx = 0) {
   const int n_pix = (x1 - x0 + 1) * (y1 - y0 + 1);
   float w[24];
   const float qnan = __uint_as_float(0x7fc00000u);
@@ -423,6 +428,11 @@ __device__ __forceinline__ void write_record_f32(float* __restrict__ outw, float
   float4* o4 = reinterpret_cast<float4*>(outw);
 #pragma unroll
   for (int i = 0; i < 6; ++i) o4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  for (int p = 0; p < n_peer; ++p) {
+    float4* d4 = reinterpret_cast<float4*>(peers[p] + peer_idx);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
 }
 
 

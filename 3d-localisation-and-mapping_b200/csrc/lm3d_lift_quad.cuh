@@ -693,8 +693,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
         tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
         write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
                          tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
-                         (float)(1.0 / A.scale_depth));
-        push_record(A, b);
+                         (float)(1.0 / A.scale_depth), A.peer, A.n_peer, A.peer_off + b);
       }
       __syncwarp();
     }

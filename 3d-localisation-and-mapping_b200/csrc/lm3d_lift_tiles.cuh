@@ -44,8 +44,12 @@ constexpr int kTileSample = LM3D_TILE_SAMPLE;  // lattice sample per box
 #define LM3D_TILE_BATCH 4
 #endif
 constexpr int kTileBatch = LM3D_TILE_BATCH;    // loads a thread issues together (strip row steps, tile quads)
+#ifndef LM3D_TILE_RING
+#define LM3D_TILE_RING 4   // cp.async slots per thread in the scan passes (measured on C3 / C5: 4 with 3 CTAs per SM beats 2, 8, 16 and 2 CTAs)
+#endif
+#define LM3D_TILE_RING_ LM3D_TILE_RING
 constexpr int kTileHistWords = 256 + kBlkBins + 256;
-constexpr int kTileBoxSmemWords = kTileHistWords + kSortCap + kTileMaxInt;
+constexpr int kTileBoxSmemWords = kTileHistWords + kSortCap + kTileMaxInt + 16 + kBlkThreads * 4 * LM3D_TILE_RING_;
 
 struct __align__(16) TileSum {   // 64 bytes
   int32_t n_valid;
@@ -219,12 +223,18 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
           vr += frp;
         } else {
           const uint32_t bits[4] = {q0.x, q0.y, q0.z, q0.w};
+          float y[4];
+          unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+          unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+          const uint32_t u[4] = {__float_as_uint(y[0]) - tgt, __float_as_uint(y[1]) - tgt, __float_as_uint(y[2]) - tgt,
+                                 __float_as_uint(y[3]) - tgt};
+          if (min(min(u[0], u[1]), min(u[2], u[3])) <= dt) {  // one branch per quad
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float y = fmaf(__uint_as_float(bits[j]), s4f, kkf);
-            if ((__float_as_uint(y) - tgt) <= dt && key_valid(bits[j], dm[j])) {
-              const int pos = atomicAdd(ncoll, 1);
-              if (pos < kTileCollCap) sortbuf[pos] = bits[j];
+            for (int j = 0; j < 4; ++j) {
+              if (u[j] <= dt && key_valid(bits[j], dm[j])) {
+                const int pos = atomicAdd(ncoll, 1);
+                if (pos < kTileCollCap) sortbuf[pos] = bits[j];
+              }
             }
           }
         }
@@ -242,33 +252,45 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
 // a tile go to 64 consecutive threads, so a thread keeps ONE (row, quad column) position and walks the tiles four
 // apart: a load costs one shared-memory read of the tile's offset and one add.  kTileScanBatch loads in flight.
 // MODE 0: histogram update, MODE 1: collect the keys whose histogram word lies in [tgt, tgt + dt].
-#ifndef LM3D_TILE_SCAN_BATCH
-#define LM3D_TILE_SCAN_BATCH 4
-#endif
-constexpr int kTileScanBatch = LM3D_TILE_SCAN_BATCH;
+constexpr int kTileRing = LM3D_TILE_RING;
 template <int MODE>
 __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, int W, const uint32_t* scan_list, int n_scan,
                                                uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
-                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
+                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll, uint32_t ring_s) {
+  // cp.async ring: the thread's quad of tile m + kTileRing is requested (LDGSTS, no registers held) before its quad
+  // of tile m is reduced -- eight 16-byte loads in flight per thread.  The kernel is bound by load latency (ncu: a
+  // third of the issue slots used, long-scoreboard the top stall) and register-held batches cap the loads in
+  // flight at the register budget; the ring does not.  Measured on C3 x 200 frames: 2.82 ms with register batches of 4, 2.27 ms with the ring.
   const float* __restrict__ qp = fbase + (((threadIdx.x & 63) >> 2) * W + (threadIdx.x & 3) * 4);  // (row, quad column) inside a tile
-  constexpr int kLanes = kBlkThreads / kTileQuads;  // tiles in flight per step (4)
+  const int g = threadIdx.x >> 6;                      // the 64-thread group takes tiles g, g + 4, g + 8, ...
+  const int n_my = (n_scan - g + 3) >> 2;              // (same for the 64 threads of a group: warp-uniform control)
+  constexpr uint32_t kSlot = kBlkThreads * 16;
+#pragma unroll
+  for (int i = 0; i < kTileRing; ++i) {
+    const bool ok = i < n_my;
+    cp_async_16(ring_s + i * kSlot, qp + (ok ? scan_list[g + 4 * i] : 0u), ok ? 16u : 0u);
+    cp_async_commit();
+  }
 #pragma unroll 1
-  for (int t0 = threadIdx.x >> 6; t0 < n_scan; t0 += kTileScanBatch * kLanes) {
-    uint4 qb[kTileScanBatch];
+  for (int m0 = 0; m0 < n_my; m0 += kTileRing) {
 #pragma unroll
-    for (int i = 0; i < kTileScanBatch; ++i) {
-      const int t = t0 + i * kLanes;
-      if (t < n_scan) qb[i] = ldg_u4(qp + scan_list[t]);
-    }
-#pragma unroll
-    for (int i = 0; i < kTileScanBatch; ++i) {
-      if (t0 + i * kLanes >= n_scan) break;
-      const uint32_t bits[4] = {qb[i].x, qb[i].y, qb[i].z, qb[i].w};
+    for (int i = 0; i < kTileRing; ++i) {
+      const int m = m0 + i;
+      if (m >= n_my) break;
+      cp_async_wait<kTileRing - 1>();
+      const uint4 q = lds_u4(ring_s + i * kSlot);
+      {
+        const int mn = m + kTileRing;
+        const bool ok = mn < n_my;
+        cp_async_16(ring_s + i * kSlot, qp + (ok ? scan_list[g + 4 * mn] : 0u), ok ? 16u : 0u);
+        cp_async_commit();
+      }
+      const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+      float y[4];
       if (MODE == 0) {
         uint32_t key[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) key[j] = key_valid(bits[j], dmax_bits) ? bits[j] : 0x7fffffffu;
-        float y[4];
         unpack2(fma2(pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
         unpack2(fma2(pack2(__uint_as_float(key[2]), __uint_as_float(key[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
 #pragma unroll
@@ -277,23 +299,28 @@ __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, 
           asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias) : "memory");
         }
       } else {
-        float y[4];
         unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
         unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+        // one branch per quad: the smallest distance to the target words decides whether any pixel can match
+        const uint32_t u[4] = {__float_as_uint(y[0]) - tgt, __float_as_uint(y[1]) - tgt, __float_as_uint(y[2]) - tgt,
+                               __float_as_uint(y[3]) - tgt};
+        if (min(min(u[0], u[1]), min(u[2], u[3])) <= dt) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if ((__float_as_uint(y[j]) - tgt) <= dt && key_valid(bits[j], dmax_bits)) {
-            const int pos = atomicAdd(ncoll, 1);
-            if (pos < kTileCollCap) sortbuf[pos] = bits[j];
+          for (int j = 0; j < 4; ++j) {
+            if (u[j] <= dt && key_valid(bits[j], dmax_bits)) {
+              const int pos = atomicAdd(ncoll, 1);
+              if (pos < kTileCollCap) sortbuf[pos] = bits[j];
+            }
           }
         }
       }
     }
   }
+  cp_async_wait<0>();  // drain the (zero-size) requests past the end before the slots are reused
 }
 
 #ifndef LM3D_TILE_MINB
-#define LM3D_TILE_MINB 2   // 2 x 256 threads at up to 128 registers: measured 2.62 ms vs 3.69 ms (3 CTAs, 80 registers, spills) on C3 x 200
+#define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers (32 bytes of spills) beats 2 CTAs at 124 and 4 at 64 (C3 x 200: 2.27 / 2.41 / 2.41 ms)
 #endif
 __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -304,6 +331,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
   const LiftArgs& A = T.A;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(scan_list + kTileMaxInt + 16) + (uint32_t)tid * 16;
   const int W = A.W, H = A.H;
   const int n_tiles = T.ntx * T.nty;
   const int b_begin = (int)T.frame_off[T.f0], b_end = (int)T.frame_off[T.f0 + T.nf];
@@ -413,7 +441,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     const int nv_strips_l = (int)acc.n_valid;
     __syncthreads();
     const int n_scan = sh.n_scan;
-    tile_scan_pass<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr);
+    tile_scan_pass<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_s);
 
     // ---- block reduction -----------------------------------------------------------------------------------
     {
@@ -500,7 +528,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
         for (int s = 0; s < n_sr; ++s)
           tile_rect_pass<1>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
                             acc, d0, d1, tgt, dt, sortbuf, &sh.ncoll);
-        tile_scan_pass<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll);
+        tile_scan_pass<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_s);
         __syncthreads();
         if (sh.ncoll != n_coll) {
           handover = true;  // (cannot happen: both passes evaluate the same map)

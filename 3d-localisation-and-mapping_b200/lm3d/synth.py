@@ -119,7 +119,10 @@ class ArrayDataset:
         """Batched form used by the drop-in ``ProcessPose``: depth of ``frames`` into ``depth_out [n,H,W]``,
         returns ``[n,6]`` = fx, fy, cx, cy, image_width, image_height (RGB resolution)."""
         idx = np.asarray(frames, dtype=np.int64)
-        np.take(self.depth, idx, axis=0, out=depth_out)
+        if len(idx) and int(idx[-1]) - int(idx[0]) + 1 == len(idx) and (len(idx) == 1 or bool(np.all(np.diff(idx) == 1))):
+            depth_out[...] = self.depth[int(idx[0]) : int(idx[-1]) + 1]  # consecutive frames: one block copy
+        else:
+            np.take(self.depth, idx, axis=0, out=depth_out)
         cal = np.empty((len(idx), 6), dtype=np.float64)
         for i, f in enumerate(idx):
             ci = self.intrinsics[int(f)]

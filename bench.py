@@ -251,7 +251,9 @@ def pin_to_gpu_numa_node(local: int):
         bus = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{getattr(prop, 'pci_device_id', 0):02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         if node < 0:
-            return {"numa_node": None, "note": "no NUMA affinity reported for the GPU"}
+            n_nodes = len(glob.glob("/sys/devices/system/node/node[0-9]*"))
+            return {"numa_node": None, "note": f"no NUMA affinity reported for the GPU ({n_nodes} NUMA node(s) visible, "
+                                               f"{len(os.sched_getaffinity(0))} CPUs allowed): nothing to pin"}
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -568,8 +570,15 @@ def run_lm3d(args):
     ev1.record()
     barrier()
     launches = lib.lm3d_kernel_launches() - launches0
-    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    my_ms = ev0.elapsed_time(ev1) / args.steps
+    ms_per_step = max_over_ranks(my_ms)
     value = world * F / (ms_per_step * 1e-3)
+    ms_ranks = [my_ms]
+    if world > 1:  # the spread over ranks (every GPU lifts an independent shard of the same size)
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = my_ms
+        dist.all_reduce(t)
+        ms_ranks = [float(v) for v in t.cpu()]
 
     # ---- multi-GPU: the gathered bytes must equal the concatenation of the per-rank records (untimed) -----------------
     gather_check = None
@@ -679,6 +688,7 @@ def run_lm3d(args):
             "steps": args.steps,
             "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step,
+            "ms_per_step_by_rank": ms_ranks,
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
