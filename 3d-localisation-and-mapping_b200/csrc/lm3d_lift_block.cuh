@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
   const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
   const uint32_t coll_s = (uint32_t)__cvta_generic_to_shared(smem_u32 + kBlkHistWords) + (uint32_t)tid * 4;
   const uint32_t pipe_s = (uint32_t)__cvta_generic_to_shared(smem_u32 + kBlkHistWords + kBlkCollWords + kSortCap) + (uint32_t)tid * 16;
+#if !LM3D_BLK_BATCH
   constexpr uint32_t kSlot = kBlkThreads * 16;  // bytes between two pipeline slots of a thread
+#endif
   const int n_items = A.counters[A.count_idx];
   const int W = A.W;
 

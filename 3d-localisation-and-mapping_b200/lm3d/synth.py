@@ -116,18 +116,26 @@ class ArrayDataset:
         return None, self.depth[idx], self.intrinsics[idx]
 
     def batch(self, frames, depth_out):
-        """Batched form used by the drop-in ``ProcessPose``: depth of ``frames`` into ``depth_out [n,H,W]``,
-        returns ``[n,6]`` = fx, fy, cx, cy, image_width, image_height (RGB resolution)."""
+        """Batched form used by the drop-in ``ProcessPose``: returns ``(cal, depth)`` -- ``cal [n,6]`` = fx, fy, cx, cy,
+        image_width, image_height (RGB resolution) and the depth of ``frames`` as a C-contiguous ``[n,H,W]`` float32
+        array: a zero-copy view of the store when the frames are consecutive, else ``depth_out`` filled."""
         idx = np.asarray(frames, dtype=np.int64)
         if len(idx) and int(idx[-1]) - int(idx[0]) + 1 == len(idx) and (len(idx) == 1 or bool(np.all(np.diff(idx) == 1))):
-            depth_out[...] = self.depth[int(idx[0]) : int(idx[-1]) + 1]  # consecutive frames: one block copy
+            depth = self.depth[int(idx[0]) : int(idx[-1]) + 1]
+            if depth.dtype != np.float32 or not depth.flags.c_contiguous:
+                depth_out[...] = depth
+                depth = depth_out
         else:
             np.take(self.depth, idx, axis=0, out=depth_out)
+            depth = depth_out
         cal = np.empty((len(idx), 6), dtype=np.float64)
+        last, row = None, None
         for i, f in enumerate(idx):
             ci = self.intrinsics[int(f)]
-            cal[i] = (ci["fx"], ci["fy"], ci["cx"], ci["cy"], ci["image_width"], ci["image_height"])
-        return cal
+            if ci is not last:
+                last, row = ci, (ci["fx"], ci["fy"], ci["cx"], ci["cy"], ci["image_width"], ci["image_height"])
+            cal[i] = row
+        return cal, depth
 
 
 def _quat_mul(a, b):

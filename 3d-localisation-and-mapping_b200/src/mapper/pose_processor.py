@@ -152,19 +152,22 @@ class ProcessPose:
         return frames, frame_off, boxes, pose7
 
     def _gather_depth(self, frames, depth_out, intr4, image_wh):
-        """Depth + intrinsics of ``frames`` into the given HOST arrays.  A dataset with a ``batch(frames, out)``
-        method (the in-memory ``ArrayDataset``) fills them in one call; anything else is read frame by frame like the
-        reference does (``dataset[i]``, ``pose_processor.py:93``).  (Datasets that deliver depth on the DEVICE --
-        ``lm3d.ingest.DepthSequence`` -- take ``_lift_from_device_loader`` instead.)"""
+        """Depth + intrinsics of ``frames``: fills ``intr4`` / ``image_wh`` and returns the ``[n,H,W]`` float32 HOST
+        array to lift from.  A dataset with a ``batch(frames, out)`` method (the in-memory ``ArrayDataset``) answers in
+        one call and may hand back a zero-copy view of its own storage; anything else is read frame by frame into
+        ``depth_out`` like the reference does (``dataset[i]``, ``pose_processor.py:93``).  (Datasets that deliver
+        depth on the DEVICE -- ``lm3d.ingest.DepthSequence`` -- take ``_lift_from_device_loader`` instead.)"""
         H, W = int(self.depth_height), int(self.depth_width)
         batch = getattr(self.dataset, "batch", None)
         if batch is not None:
-            cal = batch(frames, depth_out)  # [n,6] fx fy cx cy image_width image_height
+            cal, depth = batch(frames, depth_out)  # cal [n,6]: fx fy cx cy image_width image_height
             cal = np.asarray(cal, dtype=np.float64)
+            if depth.shape != (len(frames), H, W):
+                raise ValueError(f"dataset.batch returned depth of shape {depth.shape}, expected {(len(frames), H, W)}")
             s = cal[:, 4] / float(self.depth_width)
             intr4[:] = cal[:, :4] / s[:, None]
             image_wh[:] = cal[:, 4:6]
-            return
+            return depth
         for i, frame_index in enumerate(frames):
             _rgb, depth_tensor, ci = self.dataset[frame_index]
             _, depth_image = self.visualiser.parse_images(None, depth_tensor)
@@ -175,6 +178,7 @@ class ProcessPose:
             s = ci["image_width"] / self.depth_width
             intr4[i] = (ci["fx"] / s, ci["fy"] / s, ci["cx"] / s, ci["cy"] / s)
             image_wh[i] = (ci["image_width"], ci["image_height"])
+        return depth_out
 
     def _gather(self):
         """Whole-sequence form of the two gathers above (tests, small sequences)."""
@@ -183,19 +187,25 @@ class ProcessPose:
         depth = np.empty((F, H, W), dtype=np.float32)
         intr4 = np.empty((F, 4), dtype=np.float64)
         image_wh = np.empty((F, 2), dtype=np.float64)
-        self._gather_depth(frames, depth, intr4, image_wh)
+        depth = self._gather_depth(frames, depth, intr4, image_wh)
         return frames, depth, pose7, intr4, image_wh, frame_off, boxes
+
+    _staging = {}  # (shape, dtype) -> pinned torch tensor, shared by the instances of a process (pinning 256 MB costs ~0.1 s)
 
     def _pinned(self, shape, dtype):
         """Staging buffer for one chunk: pinned when torch can pin it (H2D copies of the C call go asynchronous)."""
-        try:
-            import torch
+        key = (tuple(shape), np.dtype(dtype).name)
+        t = ProcessPose._staging.get(key)
+        if t is None:
+            try:
+                import torch
 
-            t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-            self._pin_keepalive = getattr(self, "_pin_keepalive", []) + [t]
-            return t.numpy()
-        except Exception:
-            return np.empty(shape, dtype=dtype)
+                t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+                ProcessPose._staging.clear()
+                ProcessPose._staging[key] = t
+            except Exception:
+                return np.empty(shape, dtype=dtype)
+        return t.numpy()
 
     # ------------------------------------------------------------------------------------
     def get_global_records(self) -> LiftedRecords:
@@ -219,13 +229,12 @@ class ProcessPose:
             b0, b1 = int(frame_off[f0]), int(frame_off[f1])
             if b1 == b0:
                 continue  # no boxes in this chunk: its frames are not even read
-            self._gather_depth(frames[f0:f1], depth[:n], intr4[:n], image_wh[:n])
+            d = self._gather_depth(frames[f0:f1], depth[:n], intr4[:n], image_wh[:n])
             lift.lift_boxes_host(
-                depth[:n], pose7[f0:f1], intr4[:n], boxes[b0:b1], image_wh[:n], frame_off[f0 : f1 + 1] - b0,
+                d, pose7[f0:f1], intr4[:n], boxes[b0:b1], image_wh[:n], frame_off[f0 : f1 + 1] - b0,
                 scale_depth=float(self.scale_depth), max_depth_mm=float(self.max_depth_mm),
                 q=float(self.percentile), device=int(self.device), out=rec[b0:b1],
             )
-        self._pin_keepalive = []
         return self._finish(frames, frame_off, rec)
 
     def _lift_from_device_loader(self, frames, frame_off, boxes, pose7, rec, chunk):
