@@ -22,6 +22,13 @@ constexpr int kBlkHistWords = 256 + kBlkBins + 256;  // [0,256) below, [256,1280
 constexpr int kBlkCollRows = 16;                 // thread-private column depth (+4 guard rows)
 constexpr int kBlkCollWords = kBlkThreads * (kBlkCollRows + 4);
 constexpr int kBlkCollCap = 2048;                // keys pass 2 may collect (<= kSortCap)
+#ifndef LM3D_BLK_SORTED_BRACKET
+#define LM3D_BLK_SORTED_BRACKET 0   // 1: round 1's bracket from a sorted 1024-pixel sample
+#endif
+#ifndef LM3D_BLK_BINNED_SAMPLE
+#define LM3D_BLK_BINNED_SAMPLE 2048
+#endif
+constexpr int kBlkBinnedSample = LM3D_BLK_BINNED_SAMPLE;  // lattice sample of the binned bracket
 constexpr int kBlkSample = 1024;                 // lattice sample (block bitonic sort: 55 stages of 2 elements per thread)
 constexpr int kBlkPipeWords = kBlkThreads * 4 * kQuadDepth;
 constexpr int kBlkSmemWords = kBlkHistWords + kBlkCollWords + kSortCap + kBlkPipeWords;
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
     const int b = A.list[item];
     const int f = A.box_frame[b];
     const Rect rc = load_rect(A.rect4, b, A.H, W);
-    const long long n_pix = (long long)rc.w * rc.h;
+    [[maybe_unused]] const long long n_pix = (long long)rc.w * rc.h;
     const float* __restrict__ fbase = A.depth + (size_t)f * A.H * W;
     const float4* tp = reinterpret_cast<const float4*>(A.tab + f);
     const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
@@ -73,25 +80,31 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
     tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
     tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
 
-    // ---- sample kBlkSample pixels on a lattice, sort, bracket (+-3 sigma = +-4.7 % of the keys: ~1 % of a bin each) ----
-    int svl = 0;
-    for (int i = tid; i < kBlkSample; i += kBlkThreads) {
-      const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / kBlkSample;
-      const int ry = (int)(idx / rc.w), cx = (int)(idx - (long long)ry * rc.w);
-      const uint32_t bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
-      const bool v = key_valid(bits, A.dmax_bits);
-      sortbuf[i] = v ? bits : kKeyInvalid;
-      svl += v;
-    }
-    const int sv = block_sum_i(svl, sh.ls, 0);
-    block_bitonic(sortbuf, kBlkSample);
+    // ---- lattice sample -> bracket.  Round 2: binned (no sort), and with the sort gone a 2048-pixel sample is cheap ----
     uint32_t lo = 1u, hi = kKeyMaxValid;
-    if (sv > 0) {
-      int a, bb;
-      bracket_ranks(sv, A.quant, kBracketZ, a, bb);
-      if (a >= 0) lo = sortbuf[a];
-      if (bb < sv) hi = sortbuf[bb];
+#if LM3D_BLK_SORTED_BRACKET
+    {
+      int svl = 0;
+      for (int i = tid; i < kBlkSample; i += kBlkThreads) {
+        const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / kBlkSample;
+        const int ry = (int)(idx / rc.w), cx = (int)(idx - (long long)ry * rc.w);
+        const uint32_t bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+        const bool v = key_valid(bits, A.dmax_bits);
+        sortbuf[i] = v ? bits : kKeyInvalid;
+        svl += v;
+      }
+      const int sv = block_sum_i(svl, sh.ls, 0);
+      block_bitonic(sortbuf, kBlkSample);
+      if (sv > 0) {
+        int a, bb;
+        bracket_ranks(sv, A.quant, kBracketZ, a, bb);
+        if (a >= 0) lo = sortbuf[a];
+        if (bb < sv) hi = sortbuf[bb];
+      }
     }
+#else
+    block_bracket_binned<kBlkBinnedSample>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, hist, sh.ls, lo, hi);
+#endif
     hi = min(hi, A.dmax_bits);
     float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
     float s4f, kkf;
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
 #pragma unroll
             for (int i = 0; i < kBlkBatch; ++i) {
               if (st + i >= nsteps) break;
-              collect_quad<kBlkThreads * 4>(qb[i], s4f, kkf, tg, dt, cptr);
+              collect_quad<kBlkThreads * 4, true>(qb[i], s4f, kkf, tg, dt, cptr);
               cptr = min(cptr, cend);
             }
           }
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_BLK_MINB) lift_block_kernel(
               cp_async_commit();
               gp += rstep;
               nxt_row += RPq;
-              collect_quad<kBlkThreads * 4>(q0, s4f, kkf, tg, dt, cptr);
+              collect_quad<kBlkThreads * 4, true>(q0, s4f, kkf, tg, dt, cptr);
               cptr = min(cptr, cend);
             }
           }

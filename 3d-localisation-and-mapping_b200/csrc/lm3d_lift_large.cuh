@@ -58,6 +58,75 @@ __device__ void block_bitonic(uint32_t* buf, int n) {
   __syncthreads();
 }
 
+// Bracket of the target quantile from a lattice sample of the rect WITHOUT sorting it (round 2): NS samples (NS / 256
+// per thread, kept in registers) are binned into 1024 bins in key space between the sample's smallest and largest key
+// (`scratch`: 1024 zeroable words), a block scan turns the counts into ranks, and the bracket is the lower edge of the
+// bin holding sample rank a and the upper edge of the bin holding rank b (bracket_ranks: +-z sigma of the sample
+// rank).  The block bitonic sort it replaces was 8-13 % of the CTA kernels' instructions and most of their barriers;
+// the bracket only steers which keys land in the histogram bins, never the result.
+template <int NS>
+__device__ void block_bracket_binned(const float* __restrict__ fbase, int W, const Rect& rc, uint32_t dmax_bits, double quant,
+                                     float z, uint32_t* scratch, LargeShared& sh, uint32_t& lo, uint32_t& hi) {
+  constexpr int PER = NS / kLargeThreads;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_pix = (long long)rc.w * rc.h;
+  uint32_t s[PER];
+  uint32_t kmn = kKeyInvalid, kmx = 0u;
+  int svl = 0;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int i = e * kLargeThreads + tid;
+    const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / NS;
+    const int ry = (int)(idx / rc.w), cx = (int)(idx - (long long)ry * rc.w);
+    const uint32_t bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
+    const bool v = key_valid(bits, dmax_bits);
+    s[e] = v ? bits : kKeyInvalid;
+    if (v) { kmn = min(kmn, bits); kmx = max(kmx, bits); }
+    svl += v;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) scratch[i * kLargeThreads + tid] = 0u;
+  const int sv = block_sum_i(svl, sh, 0);
+  block_minmax_u(kmn, kmx, sh);
+  lo = 1u; hi = kKeyMaxValid;
+  if (sv == 0) return;  // (uniform)
+  const uint32_t span = kmx - kmn;
+  const int shift = max(0, 22 - __clz(span | 1u));  // (span >> shift) <= 1023
+#pragma unroll
+  for (int e = 0; e < PER; ++e)
+    if (s[e] != kKeyInvalid) atomicAdd(&scratch[(s[e] - kmn) >> shift], 1u);
+  __syncthreads();
+  const uint4 h4 = reinterpret_cast<const uint4*>(scratch)[tid];
+  const int c4[4] = {(int)h4.x, (int)h4.y, (int)h4.z, (int)h4.w};
+  const int c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh.red_i[warp][1] = incl;
+  if (tid == 0) { sh.bc_i[0] = -1; sh.bc_i[1] = -1; }
+  __syncthreads();
+  int wpre = 0;
+#pragma unroll
+  for (int w = 0; w < kLargeWarps; ++w) if (w < warp) wpre += sh.red_i[w][1];
+  int a, b;
+  bracket_ranks(sv, quant, z, a, b);
+  int cum = wpre + incl - c;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (a >= cum && a < cum + c4[i]) sh.bc_i[0] = 4 * tid + i;
+    if (b >= cum && b < cum + c4[i]) sh.bc_i[1] = 4 * tid + i;
+    cum += c4[i];
+  }
+  __syncthreads();
+  const int ba = sh.bc_i[0], bb = sh.bc_i[1];
+  if (a >= 0 && ba >= 0) lo = max(kmn + ((uint32_t)ba << shift), 1u);
+  if (b < sv && bb >= 0) hi = min(kmn + (((uint32_t)bb + 1u) << shift) - 1u, kmx);
+  __syncthreads();
+}
+
 // Key sources for the block-level window search
 struct RectSource {
   const float* fbase; int W; Rect rc; uint32_t dmax_bits;

@@ -36,8 +36,12 @@ constexpr int kQuadWarps = LM3D_QUAD_WARPS;
 #define LM3D_QUAD_P2_LDG 0  // 1: pass 2 through plain LDG.128 with a one-step register prefetch instead of cp.async
                             // (measured on C2: 1.43 ms vs 1.22 ms -- one step of distance does not cover an L2 hit)
 #endif
+#ifndef LM3D_QUAD_BINNED_BRACKET
+#define LM3D_QUAD_BINNED_BRACKET 1  // 1: bracket from a 32-bin histogram of the lattice sample; 0: from the sorted sample (round 1)
+#endif
 #ifndef LM3D_QUAD_SAMPLE_E
-#define LM3D_QUAD_SAMPLE_E 2  // lattice sample = 32 * E pixels
+#define LM3D_QUAD_SAMPLE_E 4  // lattice sample = 32 * E pixels (2 with the sorted bracket of round 1; the binned bracket makes 128 samples cheap:
+                              // C2 1.240 ms sorted E=2, 1.200 binned E=2, 1.178 binned E=4, 1.207 E=6, 1.229 E=8)
 #endif
 constexpr int kQuadDepth = LM3D_QUAD_DEPTH;                // row steps a lane keeps in flight in pass 1 (cp.async groups)
 #ifndef LM3D_QUAD_DEPTH2
@@ -125,13 +129,31 @@ __device__ __forceinline__ uint4 ldg_u4(const float* p) { return __ldg(reinterpr
 
 // pass 2 on one quad: two packed fmas give the four bin words; a pixel whose word is tg[j] (+ dt) is appended to the
 // lane's private column.  tg[j] - dt wraps for masked pixels (tg = 0xffffff00), which then match nothing.
-template <int STRIDE>
+template <int STRIDE, bool BRANCH = false>
 __device__ __forceinline__ void collect_quad(const uint4 q, float s4f, float kkf, const uint32_t (&tg)[4], uint32_t dt,
                                              uint32_t& ptr) {
   float y[4];
   unpack2(fma2(pack2(__uint_as_float(q.x), __uint_as_float(q.y)), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
   unpack2(fma2(pack2(__uint_as_float(q.z), __uint_as_float(q.w)), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
   const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+  // BRANCH (lift_block_kernel: 3.81 -> 3.33 ms on C3 x 200; lift_quad_kernel gets SLOWER with it, 1.176 -> 1.234 ms):
+  // one test per QUAD: the smallest distance of the four words to their targets decides whether any pixel can match
+  // (a few per cent of the quads); the predicated store + bump per pixel of the branch-free form below costs three
+  // instructions per pixel whether or not anything matches
+  if constexpr (BRANCH) {
+    const uint32_t u0 = __float_as_uint(y[0]) - tg[0], u1 = __float_as_uint(y[1]) - tg[1], u2 = __float_as_uint(y[2]) - tg[2],
+                   u3 = __float_as_uint(y[3]) - tg[3];
+    if (min(min(u0, u1), min(u2, u3)) <= dt) {
+      const uint32_t u[4] = {u0, u1, u2, u3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (u[j] <= dt) {
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(bits[j]) : "memory");
+          ptr += STRIDE;
+        }
+    }
+    return;
+  }
   if (dt == 0u) {  // (uniform) the usual case: both ranks in one bin -> one compare per pixel
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -315,7 +337,11 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
       hi = min(hi, A.dmax_bits);
       clo = max(clo, lo); chi = min(chi, hi);
 #else
+#if LM3D_QUAD_BINNED_BRACKET
+      if (n_pix > 64) sample_bracket_binned<LM3D_QUAD_SAMPLE_E>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, hist, lo, hi);
+#else
       if (n_pix > 64) sample_bracket_regs<LM3D_QUAD_SAMPLE_E>(fbase, W, rc, A.dmax_bits, A.quant, kBracketZ, lane, lo, hi);
+#endif
       hi = min(hi, A.dmax_bits);
 #endif
       // the bracket as depths [wlo_f, whi_f]; 250 of the 256 bins span it (see 3b for the map)

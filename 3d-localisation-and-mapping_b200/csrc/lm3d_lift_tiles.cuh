@@ -37,9 +37,13 @@ constexpr int kTileQuads = kTile * kTile / 4;  // float4 quads per tile (64)
 constexpr int kTileMaxInt = 4096;            // completely covered tiles per box the scan list holds
 constexpr int kTileCollCap = 2048;           // keys of the target bins a box may collect
 #ifndef LM3D_TILE_SAMPLE
-#define LM3D_TILE_SAMPLE 512
+#define LM3D_TILE_SAMPLE 2048
 #endif
 constexpr int kTileSample = LM3D_TILE_SAMPLE;  // lattice sample per box
+#ifndef LM3D_TILE_BRACKET_Z
+#define LM3D_TILE_BRACKET_Z 3.0f
+#endif
+constexpr float kTileBracketZ = LM3D_TILE_BRACKET_Z;  // bracket half-width in sample sigmas: a miss costs a hand-over to lift_block_kernel
 #ifndef LM3D_TILE_BATCH
 #define LM3D_TILE_BATCH 4
 #endif
@@ -352,26 +356,9 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     const FrameTab tb = load_tab(A.tab, f);
     const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
 
-    // ---- sample kTileSample pixels on a lattice, sort, bracket (as lift_block_kernel, half its sample: the sort is
-    //      13 % of this kernel's instructions at 1024; +-3 sigma of 512 = +-6.9 % of the keys, ~25 per histogram bin) ----
-    int svl = 0;
-    for (int i = tid; i < kTileSample; i += kBlkThreads) {
-      const long long idx = ((long long)i * n_pix + (n_pix >> 1)) / kTileSample;
-      const int ry = (int)(idx / rc.w), cx = (int)(idx - (long long)ry * rc.w);
-      const uint32_t bits = __float_as_uint(__ldg(fbase + (size_t)(rc.y0 + ry) * W + rc.x0 + cx));
-      const bool v = key_valid(bits, A.dmax_bits);
-      sortbuf[i] = v ? bits : kKeyInvalid;
-      svl += v;
-    }
-    const int sv = block_sum_i(svl, sh.ls, 0);
-    block_bitonic(sortbuf, kTileSample);
+    // ---- lattice sample -> bracket [lo, hi] in key space (binned, no sort: block_bracket_binned) --------------------
     uint32_t lo = 1u, hi = kKeyMaxValid;
-    if (sv > 0) {
-      int a, bb;
-      bracket_ranks(sv, A.quant, kBracketZ, a, bb);
-      if (a >= 0) lo = sortbuf[a];
-      if (bb < sv) hi = sortbuf[bb];
-    }
+    block_bracket_binned<kTileSample>(fbase, W, rc, A.dmax_bits, A.quant, kTileBracketZ, hist, sh.ls, lo, hi);
     hi = min(hi, A.dmax_bits);
     const float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
     const float wd = whi_f - wlo_f;

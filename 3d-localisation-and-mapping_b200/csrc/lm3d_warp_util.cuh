@@ -158,6 +158,58 @@ __device__ __forceinline__ void sample_bracket_regs(const float* __restrict__ fb
   if (b < sv) hi = sb;
 }
 
+// The same bracket WITHOUT the sort (round 2): the 32 * E samples are binned into 32 bins in key space between the
+// sample's smallest and largest key (one shared-memory atomic per sample, `scratch` = 32 zeroable words of the warp),
+// a five-step shuffle scan turns the bin counts into ranks, and the bracket is the lower edge of the bin holding
+// sample rank a and the upper edge of the bin holding rank b.  At most one bin (1/32 of the sample's key range) wider
+// on either side than the sorted sample's bracket -- which only changes how many keys land in a histogram bin later,
+// never the result -- for ~70 instead of ~400 warp instructions per box (the sort was 7.5 % of lift_quad_kernel).
+template <int E>
+__device__ __forceinline__ void sample_bracket_binned(const float* __restrict__ fbase, int W, const Rect& rc,
+                                                      uint32_t dmax_bits, double quant, float z, int lane,
+                                                      uint32_t* scratch, uint32_t& lo, uint32_t& hi) {
+  uint32_t s[E];
+  uint32_t kmn = kKeyInvalid, kmx = 0u;
+  int sv = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    const int ic = i & 7, ir = i >> 3;
+    const int cx = ((2 * ic + 1) * rc.w) >> 4;
+    const int ry = ((2 * ir + 1) * rc.h) / (8 * E);
+    const uint32_t bits = __float_as_uint(__ldg(fbase + (uint32_t)((rc.y0 + ry) * W + rc.x0 + cx)));
+    const bool v = key_valid(bits, dmax_bits);
+    s[e] = v ? bits : kKeyInvalid;
+    if (v) { kmn = min(kmn, bits); kmx = max(kmx, bits); }
+    sv += v;
+  }
+  sv = warp_sum_i(sv);
+  if (sv == 0) return;
+  kmn = warp_min_u(kmn);
+  kmx = warp_max_u(kmx);
+  const uint32_t span = kmx - kmn;
+  const int shift = max(0, 27 - __clz(span | 1u));  // (span >> shift) <= 31
+  scratch[lane] = 0u;
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (s[e] != kKeyInvalid) atomicAdd(&scratch[(s[e] - kmn) >> shift], 1u);
+  __syncwarp();
+  const int c = (int)scratch[lane];
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int a, b;
+  bracket_ranks(sv, quant, z, a, b);
+  const uint32_t ma = __ballot_sync(kFull, a >= incl - c && a < incl), mb = __ballot_sync(kFull, b >= incl - c && b < incl);
+  if (a >= 0 && ma) lo = max(kmn + ((uint32_t)(__ffs(ma) - 1) << shift), 1u);
+  if (b < sv && mb) hi = min(kmn + (((uint32_t)__ffs(mb)) << shift) - 1u, kmx);
+  __syncwarp();
+}
+
 // Same, and also the sample values at the target rank -/+ zc sigma (zc < z): the capture window of lift_quad_kernel.
 template <int E>
 __device__ __forceinline__ void sample_bracket_regs2(const float* __restrict__ fbase, int W, const Rect& rc,

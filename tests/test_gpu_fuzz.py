@@ -82,7 +82,7 @@ def _lattice_mask(n_pix, samples):
 
 
 def test_block_kernel_refinement_and_bisection_paths_are_reached(cuda_device, monkeypatch):
-    """lift_block_kernel brackets the percentile from a 1024-pixel LATTICE sample of the rect.  Poisoning exactly the
+    """lift_block_kernel brackets the percentile from a 2048-pixel LATTICE sample of the rect.  Poisoning exactly the
     lattice pixels puts the bracket far from the true median: the histogram pass reports a miss, two refinement
     passes follow (counter 5), and when those miss too the bisection select finishes (counter 4) -- exact either way."""
     monkeypatch.setenv("LM3D_TILE_PATH", "off")
@@ -90,7 +90,7 @@ def test_block_kernel_refinement_and_bisection_paths_are_reached(cuda_device, mo
     rng = np.random.default_rng(3)
     depth = (1000 + 50 * rng.random((3, H, W))).astype(np.float32)
     rect = (0, 0, W - 1, H - 1)
-    lat = _lattice_mask(H * W, 1024).reshape(H, W)
+    lat = _lattice_mask(H * W, 2048).reshape(H, W)   # kBlkBinnedSample (csrc/lm3d_lift_block.cuh)
     n_lat = int(lat.sum())
     depth[0][lat] = (30000.0 + 100.0 * rng.random(n_lat)).astype(np.float32)  # bracket at 30 m: the rank is far below -> two refinements miss -> bisection
     depth[1][lat] = (1.0 + rng.random(n_lat)).astype(np.float32)             # bracket at 1 mm: the rank is far above it
