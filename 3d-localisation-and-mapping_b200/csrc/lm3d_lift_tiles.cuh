@@ -53,7 +53,22 @@ constexpr int kTileBatch = LM3D_TILE_BATCH;    // loads a thread issues together
 #endif
 #define LM3D_TILE_RING_ LM3D_TILE_RING
 constexpr int kTileHistWords = 256 + kBlkBins + 256;
-constexpr int kTileBoxSmemWords = kTileHistWords + kSortCap + kTileMaxInt + 16 + kBlkThreads * 4 * LM3D_TILE_RING_;
+#ifndef LM3D_TILE_STAGE
+#define LM3D_TILE_STAGE 4
+#endif
+#ifndef LM3D_TILE_TMA_RING
+#define LM3D_TILE_TMA_RING 2
+#endif
+#define LM3D_TILE_STAGE_ LM3D_TILE_STAGE
+#define LM3D_TILE_TMA_RING_ LM3D_TILE_TMA_RING
+#ifndef LM3D_TILE_FEED
+#define LM3D_TILE_FEED 0   // scan-pass feed: 0 = per-thread cp.async ring (default), 1 = TMA bulk copies (64-byte rows), 2 = TMA tensor tiles
+                           // (16 x 16 x 1 boxes of depth[F,H,W]), both into an mbarrier ring per 64-thread group.  Measured on C3 x 200
+                           // frames (all parity-green): ring 2.16 ms, tensor tiles 2.74 ms (4 tiles per stage, 2 stages; 3.07 with one tile
+                           // per stage), bulk rows 4.71 ms -- a 16 x 16 tile is 4 pixels per thread: the barrier wait + group barrier per
+                           // stage cost more than the 64 LDGSTS they replace, and 64-byte bulk copies swamp the TMA unit
+#endif
+constexpr int kTileBoxSmemWords = kTileHistWords + kSortCap + kTileMaxInt + 16 + (LM3D_TILE_FEED ? 4 * LM3D_TILE_TMA_RING_ * LM3D_TILE_STAGE_ * 256 + 2 * 4 * LM3D_TILE_TMA_RING_ + 32 : kBlkThreads * 4 * LM3D_TILE_RING_);
 
 struct __align__(16) TileSum {   // 64 bytes
   int32_t n_valid;
@@ -257,6 +272,110 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
 // apart: a load costs one shared-memory read of the tile's offset and one add.  kTileScanBatch loads in flight.
 // MODE 0: histogram update, MODE 1: collect the keys whose histogram word lies in [tgt, tgt + dt].
 constexpr int kTileRing = LM3D_TILE_RING;
+// what a scan pass does with one quad of a listed tile (MODE 0: histogram update, MODE 1: collect)
+template <int MODE>
+__device__ __forceinline__ void tile_scan_quad(const uint4 q, uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi,
+                                               uint32_t hist_bias, uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
+  const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+  float y[4];
+  if (MODE == 0) {
+    uint32_t key[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) key[j] = key_valid(bits[j], dmax_bits) ? bits[j] : 0x7fffffffu;
+    unpack2(fma2(pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+    unpack2(fma2(pack2(__uint_as_float(key[2]), __uint_as_float(key[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yc = fminf(fmaxf(y[j], ylo), yhi);  // NaN -> ylo
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias) : "memory");
+    }
+  } else {
+    unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
+    unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
+    // one branch per quad: the smallest distance to the target words decides whether any pixel can match
+    const uint32_t u[4] = {__float_as_uint(y[0]) - tgt, __float_as_uint(y[1]) - tgt, __float_as_uint(y[2]) - tgt,
+                           __float_as_uint(y[3]) - tgt};
+    if (min(min(u[0], u[1]), min(u[2], u[3])) <= dt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (u[j] <= dt && key_valid(bits[j], dmax_bits)) {
+          const int pos = atomicAdd(ncoll, 1);
+          if (pos < kTileCollCap) sortbuf[pos] = bits[j];
+        }
+      }
+    }
+  }
+}
+
+// TMA feed of the scan passes (LM3D_TILE_FEED = 1): a 64-thread group owns a ring of kTileRing 1 KB tile buffers, each
+// with an mbarrier.  Lane 0 of the group's first warp announces 1024 bytes (arrive.expect_tx), its lanes 0..15 issue
+// one bulk copy each (cp.async.bulk, a 64-byte tile row; SASS UBLKCP) -- 17 instructions per tile instead of 64 LDGSTS
+// with the three inserted LDS each.  The 64 threads wait on the barrier's phase, read their quad, reduce it, meet at
+// the group's named barrier (the buffer is free again) and the producer lanes refill it with the tile kTileRing ahead.
+__device__ __forceinline__ void bulk_copy_64(uint32_t dst_s, const void* src, uint32_t bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];" ::"r"(dst_s), "l"(src),
+               "r"(bar_s)
+               : "memory");
+}
+constexpr int kTileStage = LM3D_TILE_STAGE, kTileTmaRing = LM3D_TILE_TMA_RING;
+template <int MODE>
+__device__ __forceinline__ void tile_scan_pass_tma(const float* __restrict__ fbase, int W, const uint32_t* scan_list, int n_scan,
+                                                   uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
+                                                   uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll, uint32_t ring_base_s,
+                                                   uint32_t bar_base_s, uint32_t& phase, const void* tmap, int frame) {
+  const int g = threadIdx.x >> 6, t64 = threadIdx.x & 63, lane = threadIdx.x & 31;
+  const bool producer_warp = (threadIdx.x & 32) == 0;
+  const int n_my = (n_scan - g + 3) >> 2;                     // tiles g, g + 4, ... (same for the 64 threads of the group)
+  const int n_st = (n_my + kTileStage - 1) / kTileStage;      // stages of kTileStage tiles
+  constexpr uint32_t kStageBytes = kTileStage * 1024u;
+  const uint32_t buf0 = ring_base_s + (uint32_t)(g * kTileTmaRing) * kStageBytes, bar0 = bar_base_s + (uint32_t)(g * kTileTmaRing) * 8u;
+  auto issue = [&](int st, int i) {
+    const int m0 = st * kTileStage, cnt = min(kTileStage, n_my - m0);
+#if LM3D_TILE_FEED == 2
+    // one tensor-map request per tile: cp.async.bulk.tensor.3d, box 16 x 16 x 1 of depth[F,H,W] (SASS UTMALDG)
+    if (producer_warp) {
+      if (lane == 0) mbar_expect_tx(bar0 + i * 8, 1024u * (uint32_t)cnt);
+      __syncwarp();
+      if (lane < cnt) {
+        const uint32_t off = scan_list[g + 4 * (m0 + lane)];  // (ty * 16) * W + tx * 16
+        const int row = (int)(off / (uint32_t)W);
+        tma_load_tile_3d(buf0 + i * kStageBytes + lane * 1024, tmap, bar0 + i * 8, (int)off - row * W, row, frame);
+      }
+    }
+#else
+    if (producer_warp) {
+      if (lane == 0) mbar_expect_tx(bar0 + i * 8, 1024u * (uint32_t)cnt);
+      __syncwarp();
+      for (int k = 0; k < cnt; ++k)
+        if (lane < 16) bulk_copy_64(buf0 + i * kStageBytes + k * 1024 + lane * 64, fbase + scan_list[g + 4 * (m0 + k)] + lane * W, bar0 + i * 8);
+    }
+#endif
+  };
+#pragma unroll
+  for (int i = 0; i < kTileTmaRing; ++i)
+    if (i < n_st) issue(i, i);
+#pragma unroll 1
+  for (int s0 = 0; s0 < n_st; s0 += kTileTmaRing) {
+#pragma unroll
+    for (int i = 0; i < kTileTmaRing; ++i) {
+      const int st = s0 + i;
+      if (st >= n_st) break;
+      mbar_wait(bar0 + i * 8, (phase >> i) & 1u);
+      phase ^= 1u << i;
+      const int cnt = min(kTileStage, n_my - st * kTileStage);
+#pragma unroll
+      for (int k = 0; k < kTileStage; ++k)
+        if (k < cnt) tile_scan_quad<MODE>(lds_u4(buf0 + i * kStageBytes + k * 1024 + t64 * 16), dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
+      // every thread of the group has consumed stage i (named barriers 1..4: constant ids keep the CTA at 5 barriers)
+      if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+      else if (g == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+      else if (g == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+      else asm volatile("bar.sync 4, 64;" ::: "memory");
+      if (st + kTileTmaRing < n_st) issue(st + kTileTmaRing, i);
+    }
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, int W, const uint32_t* scan_list, int n_scan,
                                                uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
@@ -289,35 +408,7 @@ __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, 
         cp_async_16(ring_s + i * kSlot, qp + (ok ? scan_list[g + 4 * mn] : 0u), ok ? 16u : 0u);
         cp_async_commit();
       }
-      const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
-      float y[4];
-      if (MODE == 0) {
-        uint32_t key[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) key[j] = key_valid(bits[j], dmax_bits) ? bits[j] : 0x7fffffffu;
-        unpack2(fma2(pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
-        unpack2(fma2(pack2(__uint_as_float(key[2]), __uint_as_float(key[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float yc = fminf(fmaxf(y[j], ylo), yhi);  // NaN -> ylo
-          asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias) : "memory");
-        }
-      } else {
-        unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
-        unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
-        // one branch per quad: the smallest distance to the target words decides whether any pixel can match
-        const uint32_t u[4] = {__float_as_uint(y[0]) - tgt, __float_as_uint(y[1]) - tgt, __float_as_uint(y[2]) - tgt,
-                               __float_as_uint(y[3]) - tgt};
-        if (min(min(u[0], u[1]), min(u[2], u[3])) <= dt) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (u[j] <= dt && key_valid(bits[j], dmax_bits)) {
-              const int pos = atomicAdd(ncoll, 1);
-              if (pos < kTileCollCap) sortbuf[pos] = bits[j];
-            }
-          }
-        }
-      }
+      tile_scan_quad<MODE>(q, dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
     }
   }
   cp_async_wait<0>();  // drain the (zero-size) requests past the end before the slots are reused
@@ -326,7 +417,7 @@ __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, 
 #ifndef LM3D_TILE_MINB
 #define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers (32 bytes of spills) beats 2 CTAs at 124 and 4 at 64 (C3 x 200: 2.27 / 2.41 / 2.41 ms)
 #endif
-__global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T) {
+__global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* hist = smem_u32;                           // [256 | kBlkBins | 256] as in lift_block_kernel
   uint32_t* sortbuf = smem_u32 + kTileHistWords;       // [kSortCap]: lattice sample, then the collected keys
@@ -335,7 +426,15 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
   const LiftArgs& A = T.A;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(scan_list + kTileMaxInt + 16) + (uint32_t)tid * 16;
+  [[maybe_unused]] const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(scan_list + kTileMaxInt + 16) + (uint32_t)tid * 16;
+  [[maybe_unused]] const uint32_t ring_base_s = ((uint32_t)__cvta_generic_to_shared(scan_list + kTileMaxInt + 16) + 127u) & ~127u;  // (TMA tiles land 128-byte aligned)
+  [[maybe_unused]] const uint32_t bar_base_s = ring_base_s + 4u * kTileTmaRing * kTileStage * 1024u;  // 4 groups x kTileTmaRing mbarriers (8 bytes each)
+  [[maybe_unused]] uint32_t tma_phase = 0u;  // parity of every ring barrier (a bit per stage), carried across passes and boxes
+#if LM3D_TILE_FEED
+  if (tid < 4 * kTileTmaRing) mbar_init(bar_base_s + tid * 8, 1);
+  mbar_fence_init();
+  __syncthreads();
+#endif
   const int W = A.W, H = A.H;
   const int n_tiles = T.ntx * T.nty;
   const int b_begin = (int)T.frame_off[T.f0], b_end = (int)T.frame_off[T.f0 + T.nf];
@@ -428,7 +527,11 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     const int nv_strips_l = (int)acc.n_valid;
     __syncthreads();
     const int n_scan = sh.n_scan;
+#if LM3D_TILE_FEED
+    tile_scan_pass_tma<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_base_s, bar_base_s, tma_phase, &tmap, f);
+#else
     tile_scan_pass<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_s);
+#endif
 
     // ---- block reduction -----------------------------------------------------------------------------------
     {
@@ -515,7 +618,11 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
         for (int s = 0; s < n_sr; ++s)
           tile_rect_pass<1>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
                             acc, d0, d1, tgt, dt, sortbuf, &sh.ncoll);
+#if LM3D_TILE_FEED
+        tile_scan_pass_tma<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_base_s, bar_base_s, tma_phase, &tmap, f);
+#else
         tile_scan_pass<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_s);
+#endif
         __syncthreads();
         if (sh.ncoll != n_coll) {
           handover = true;  // (cannot happen: both passes evaluate the same map)
