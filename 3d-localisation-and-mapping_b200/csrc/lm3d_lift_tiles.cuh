@@ -414,6 +414,14 @@ __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, 
   cp_async_wait<0>();  // drain the (zero-size) requests past the end before the slots are reused
 }
 
+// LM3D_TILE_TIMING (dev builds only): thread 0 of every CTA adds the clock64() cycles of each phase of a box to
+// g_tile_prof[phase]; tools/tile_phases.py reads them through lm3d_debug_tile_prof.
+#ifdef LM3D_TILE_TIMING
+__device__ unsigned long long g_tile_prof[16];
+#define TILE_T(ph) do { if (tid == 0) { const long long t_now = clock64(); atomicAdd(&g_tile_prof[ph], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
+#else
+#define TILE_T(ph) do { } while (0)
+#endif
 #ifndef LM3D_TILE_MINB
 #define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers (32 bytes of spills) beats 2 CTAs at 124 and 4 at 64 (C3 x 200: 2.27 / 2.41 / 2.41 ms)
 #endif
@@ -439,8 +447,12 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
   const int n_tiles = T.ntx * T.nty;
   const int b_begin = (int)T.frame_off[T.f0], b_end = (int)T.frame_off[T.f0 + T.nf];
 
+#ifdef LM3D_TILE_TIMING
+  long long t_prev = clock64();
+#endif
   while (true) {
     __syncthreads();
+    TILE_T(9);
     if (tid == 0) sh.item = b_begin + atomicAdd(T.cursor, 1);
     __syncthreads();
     const int b = sh.item;
@@ -454,11 +466,13 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     const float* __restrict__ fbase = A.depth + (size_t)f * H * W;
     const FrameTab tb = load_tab(A.tab, f);
     const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+    TILE_T(0);
 
     // ---- lattice sample -> bracket [lo, hi] in key space (binned, no sort: block_bracket_binned) --------------------
     uint32_t lo = 1u, hi = kKeyMaxValid;
     block_bracket_binned<kTileSample>(fbase, W, rc, A.dmax_bits, A.quant, kTileBracketZ, hist, sh.ls, lo, hi);
     hi = min(hi, A.dmax_bits);
+    TILE_T(1);
     const float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
     const float wd = whi_f - wlo_f;
     const float s4f = (wd > 0.f) ? fminf(4000.f / wd, 2097152.f / whi_f) : 0.f;  // 1000 bins x 4
@@ -519,6 +533,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       }
     }
 
+    TILE_T(2);
     // ---- pass 1: strips pixel by pixel, listed tiles with the light pass -----------------------------------------
     float s0_all = 0.f, su = 0.f;
     for (int s = 0; s < n_sr; ++s)
@@ -526,6 +541,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
                         acc, s0_all, su, 0u, 0u, nullptr, nullptr);
     const int nv_strips_l = (int)acc.n_valid;
     __syncthreads();
+    TILE_T(3);
     const int n_scan = sh.n_scan;
 #if LM3D_TILE_FEED
     tile_scan_pass_tma<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_base_s, bar_base_s, tma_phase, &tmap, f);
@@ -533,6 +549,10 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     tile_scan_pass<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_s);
 #endif
 
+#ifdef LM3D_TILE_TIMING
+    __syncthreads();
+#endif
+    TILE_T(4);
     // ---- block reduction -----------------------------------------------------------------------------------
     {
       const double d0 = warp_sum_d(ds0 + (double)s0_all), d1 = warp_sum_d(dsu + (double)su), d2 = warp_sum_d(dsv + (double)acc.sv);
@@ -614,16 +634,22 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
         handover = true;
       } else {
         const uint32_t tgt = 0x4C000000u + (uint32_t)b_lo, dt = (uint32_t)(b_hi - b_lo);
+        TILE_T(5);
         float d0 = 0.f, d1 = 0.f;
         for (int s = 0; s < n_sr; ++s)
           tile_rect_pass<1>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
                             acc, d0, d1, tgt, dt, sortbuf, &sh.ncoll);
+#ifdef LM3D_TILE_TIMING
+        __syncthreads();
+#endif
+        TILE_T(6);
 #if LM3D_TILE_FEED
         tile_scan_pass_tma<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_base_s, bar_base_s, tma_phase, &tmap, f);
 #else
         tile_scan_pass<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_s);
 #endif
         __syncthreads();
+        TILE_T(7);
         if (sh.ncoll != n_coll) {
           handover = true;  // (cannot happen: both passes evaluate the same map)
           if (tid == 0) atomicAdd(&A.counters[15], 1);
@@ -652,8 +678,19 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
                    rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
       push_record(A, b);
     }
+    TILE_T(8);
   }
 }
+
+#ifdef LM3D_TILE_TIMING
+}  // namespace lm3d
+extern "C" int lm3d_debug_tile_prof(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, lm3d::g_tile_prof, sizeof(lm3d::g_tile_prof));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(lm3d::g_tile_prof, z, sizeof(z)); }
+  return 0;
+}
+namespace lm3d {
+#endif
 
 // Large boxes of frames that do NOT take the tile path -> the CTA-per-box list (order-preserving within a warp).
 __global__ void tile_route_kernel(const int32_t* __restrict__ rect4, const int32_t* __restrict__ box_frame, int64_t B, int H, int W,
