@@ -159,20 +159,6 @@ static void resolve_encoder() {  // (g_init_mu held)
   }
 }
 
-// Tensor map of the tile path's scan passes: depth[F,H,W] in boxes of 16 x 16 x 1 (one TMA request per tile).
-static bool build_scan_map(const float* depth, int64_t F, int32_t H, int32_t W, CUtensorMap* map) {
-  std::lock_guard<std::mutex> lock(g_init_mu);
-  resolve_encoder();
-  memset(map, 0, sizeof(CUtensorMap));
-  if (!g_encode_tiled || (W & 3) != 0 || (((uintptr_t)depth) & 15) != 0) return false;
-  cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
-  cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTile, (cuuint32_t)kTile, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)depth, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 static int build_tile_maps(const float* depth, int64_t F, int32_t H, int32_t W, TileMaps* maps) {
   std::lock_guard<std::mutex> lock(g_init_mu);
   resolve_encoder();
@@ -446,15 +432,13 @@ static int lift_boxes_impl(const float* depth, int64_t F, int32_t H, int32_t W, 
     T.ntx = TP.ntx; T.nty = TP.nty;
     T.tsum = (TileSum*)(tile_base + TP.off_sum);
     const int n_tiles = TP.ntx * TP.nty;
-    CUtensorMap scan_map;
-    if (!build_scan_map(depth, F, H, W, &scan_map) && LM3D_TILE_FEED == 2) return LM3D_ERR_INTERNAL;
     const unsigned box_grid = (unsigned)((int64_t)dev->sms * dev->tile_ctas);
     for (int c = 0; c < TP.n_chunks; ++c) {
       T.f0 = c * TP.chunk;
       T.nf = (int)std::min<int64_t>(TP.chunk, F - T.f0);
       T.cursor = (int32_t*)(tile_base + TP.off_cursor) + c;
       tile_sum_kernel<<<dim3((unsigned)((n_tiles + kTileSumThreads - 1) / kTileSumThreads), (unsigned)T.nf), kTileSumThreads, 0, st>>>(T);
-      tile_box_kernel<<<box_grid, kBlkThreads, kTileBoxSmemWords * 4, st>>>(T, scan_map);
+      tile_box_kernel<<<box_grid, kBlkThreads, kTileBoxSmemWords * 4, st>>>(T);
       g_launches += 2;
     }
   }

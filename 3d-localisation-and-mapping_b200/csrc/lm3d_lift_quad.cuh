@@ -80,11 +80,14 @@ struct AccQ {
 };
 
 // pass 1 on one quad (4 pixels of one row, columns col0 .. col0+3)
-template <bool CAP>
+// CAP: 0 = nothing captured; 1 = lift_quad_kernel's LM3D_QUAD_CAPTURE experiment (lane-private columns); 2 = tile_box_kernel's
+// strips: a pixel whose histogram word lies in [cap_tgt, cap_tgt + cap_dt] (= any bracket bin) is appended to the block's
+// capture buffer, so that the strips need no second visit (one branch per quad; on boundary strips matches are rare)
+template <int CAP>
 __device__ __forceinline__ void accum_quad_hist(const uint4 q, const uint32_t (&dm)[4], float vr, float b0, float b1, float b2,
                                                 const f32x2 (&cA)[3], const f32x2 (&cB)[3], float s4f, float kkf, float ylo,
                                                 float yhi, uint32_t hist_bias, AccQ& A, uint32_t cap_tgt, uint32_t cap_dt,
-                                                uint32_t& cptr) {
+                                                uint32_t& cptr, uint32_t* capbuf = nullptr, int* ncap = nullptr, int cap_max = 0) {
   const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
   bool v[4];
   uint32_t key[4];
@@ -117,11 +120,23 @@ __device__ __forceinline__ void accum_quad_hist(const uint4 q, const uint32_t (&
   }
   // capture: keys whose histogram word lies in the central window go to the lane's private column (an invalid pixel
   // carries y = NaN, whose bits are far above any window)
-  if constexpr (CAP) {
+  if constexpr (CAP == 1) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       asm volatile("{\n.reg .pred p;\n.reg .b32 t;\nsub.u32 t, %2, %3;\nsetp.le.u32 p, t, %4;\n@p st.shared.u32 [%0], %1;\n@p add.u32 %0, %0, 128;\n}"
                    : "+r"(cptr) : "r"(bits[j]), "r"(__float_as_uint(y[j])), "r"(cap_tgt), "r"(cap_dt) : "memory");
+  }
+  if constexpr (CAP == 2) {
+    const uint32_t u[4] = {__float_as_uint(y[0]) - cap_tgt, __float_as_uint(y[1]) - cap_tgt, __float_as_uint(y[2]) - cap_tgt,
+                           __float_as_uint(y[3]) - cap_tgt};
+    if (min(min(u[0], u[1]), min(u[2], u[3])) <= cap_dt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (u[j] <= cap_dt) {
+          const int pos = atomicAdd(ncap, 1);
+          if (pos < cap_max) capbuf[pos] = bits[j];
+        }
+    }
   }
 }
 

@@ -32,10 +32,31 @@
 
 namespace lm3d {
 
+#ifndef LM3D_TILE_RING
+#define LM3D_TILE_RING 4   // cp.async slots per thread in the scan passes
+#endif
+#define LM3D_TILE_RING_DEF LM3D_TILE_RING
 constexpr int kTile = 16;                    // tile edge in pixels
 constexpr int kTileQuads = kTile * kTile / 4;  // float4 quads per tile (64)
-constexpr int kTileMaxInt = 4096;            // completely covered tiles per box the scan list holds
-constexpr int kTileCollCap = 2048;           // keys of the target bins a box may collect
+#ifndef LM3D_TILE_MAXINT
+#define LM3D_TILE_MAXINT 4096
+#endif
+constexpr int kTileMaxInt = LM3D_TILE_MAXINT;  // completely covered tiles per box the scan list holds
+#ifndef LM3D_TILE_SCAN_LDG
+#define LM3D_TILE_SCAN_LDG 1   // scan-pass feed: 1 = LDG.128 into two register batches of four quads (ping-pong), 0 = cp.async ring through shared
+                               // memory.  The L1 data pipe is the kernel's busiest unit (ncu: 62 % of peak, 77 % max): the ring costs a quad
+                               // 4 wavefronts for the LDGSTS store + 4 for the LDS.128 on top of the 4 of the global load
+#endif
+constexpr int kTileListPad = (4 * LM3D_TILE_RING_DEF > 32) ? 4 * LM3D_TILE_RING_DEF : 32;  // zero offsets behind the list for requests past its end
+constexpr int kTileCollCap = 2048;           // keys of the target bins a box may collect (sortbuf[0, 2048))
+constexpr int kTileStripCap = kSortCap - kTileCollCap;  // in-bracket strip keys pass 1 may capture (sortbuf[2048, 4096))
+#ifndef LM3D_TILE_STRIP_CAPTURE
+#define LM3D_TILE_STRIP_CAPTURE 1  // 1: the strips' pass 1 appends the keys that fall into ANY bracket bin to a capture buffer and pass 2 reads
+                                   // that buffer instead of walking the strips again (falls back to the walk when the buffer overflows)
+#endif
+#ifndef LM3D_TILE_PREFETCH
+#define LM3D_TILE_PREFETCH 1       // 1: the strips' cache lines are requested into L2 (prefetch.global.L2) while the bracket is being found
+#endif
 #ifndef LM3D_TILE_SAMPLE
 #define LM3D_TILE_SAMPLE 2048
 #endif
@@ -53,29 +74,17 @@ constexpr int kTileBatch = LM3D_TILE_BATCH;    // loads a thread issues together
 #endif
 #define LM3D_TILE_RING_ LM3D_TILE_RING
 constexpr int kTileHistWords = 256 + kBlkBins + 256;
-#ifndef LM3D_TILE_STAGE
-#define LM3D_TILE_STAGE 4
-#endif
-#ifndef LM3D_TILE_TMA_RING
-#define LM3D_TILE_TMA_RING 2
-#endif
-#define LM3D_TILE_STAGE_ LM3D_TILE_STAGE
-#define LM3D_TILE_TMA_RING_ LM3D_TILE_TMA_RING
-#ifndef LM3D_TILE_FEED
-#define LM3D_TILE_FEED 0   // scan-pass feed: 0 = per-thread cp.async ring (default), 1 = TMA bulk copies (64-byte rows), 2 = TMA tensor tiles
-                           // (16 x 16 x 1 boxes of depth[F,H,W]), both into an mbarrier ring per 64-thread group.  Measured on C3 x 200
-                           // frames (all parity-green): ring 2.16 ms, tensor tiles 2.74 ms (4 tiles per stage, 2 stages; 3.07 with one tile
-                           // per stage), bulk rows 4.71 ms -- a 16 x 16 tile is 4 pixels per thread: the barrier wait + group barrier per
-                           // stage cost more than the 64 LDGSTS they replace, and 64-byte bulk copies swamp the TMA unit
-#endif
-constexpr int kTileBoxSmemWords = kTileHistWords + kSortCap + kTileMaxInt + 16 + (LM3D_TILE_FEED ? 4 * LM3D_TILE_TMA_RING_ * LM3D_TILE_STAGE_ * 256 + 2 * 4 * LM3D_TILE_TMA_RING_ + 32 : kBlkThreads * 4 * LM3D_TILE_RING_);
+// (Round 2 also measured TMA feeds for the scan passes -- 64-byte bulk rows and 16 x 16 x 1 tensor tiles into an mbarrier ring per
+// 64-thread group: 4.71 ms and 2.74 ms on C3 x 200 frames against 2.16 ms for the ring; a tile is 4 pixels per thread, so the
+// barrier wait + group barrier per stage cost more than the 64 LDGSTS they replace.  Removed; git history has them.)
 
 struct __align__(16) TileSum {   // 64 bytes
   int32_t n_valid;
   float s0, su, sv;              // sum d, sum (u - uc_t) d, sum (v - vc_t) d over the tile's valid pixels (tile-centred)
   float mn[3], mx[3];            // min / max of d (a_k u + b_k v + c_k)
   float dmin, dmax;              // smallest / largest valid depth (+inf / -inf when the tile has none)
-  float pad[4];
+  float rawmax;                  // largest non-NaN raw value of the tile, valid or not (> max_depth: the tile holds over-range pixels)
+  float pad[3];
 };
 static_assert(sizeof(TileSum) == 64, "TileSum layout");
 
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArg
   const FrameTab tb = load_tab(T.A.tab, f);
   const float uc = (float)(tx * kTile) + 7.5f, vc = (float)(ty * kTile) + 7.5f;
   float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
-  float dmn = INFINITY, dmx = -INFINITY, s0 = 0.f, su = 0.f, sv = 0.f, nv = 0.f;
+  float dmn = INFINITY, dmx = -INFINITY, s0 = 0.f, su = 0.f, sv = 0.f, nv = 0.f, rawmx = -INFINITY;
   // ray term of pixel (u, v): g_k = a_k u + b_k v + c_k, walked along a row in pairs: (g, g + a_k) += 2 a_k
   const f32x2 step0 = pack2(2.f * tb.a[0], 2.f * tb.a[0]), step1 = pack2(2.f * tb.a[1], 2.f * tb.a[1]), step2 = pack2(2.f * tb.a[2], 2.f * tb.a[2]);
   const float u0 = (float)(tx * kTile);
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArg
           g0 = add2(g0, step0); g1 = add2(g1, step1); g2 = add2(g2, step2);
           dmn = fmin3(dmn, d[2 * h], d[2 * h + 1]);
           dmx = fmax3(dmx, d[2 * h], d[2 * h + 1]);
+          rawmx = fmax3(rawmx, __uint_as_float(bits[2 * h]), __uint_as_float(bits[2 * h + 1]));
         }
       }
     }
@@ -167,22 +177,38 @@ __global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArg
   o[0] = make_float4(__int_as_float((int)nv), s0, su, sv);
   o[1] = make_float4(mn0, mn1, mn2, mx0);
   o[2] = make_float4(mx1, mx2, dmn, dmx);
+  o[3] = make_float4(rawmx, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------
-// 5b. boxes: one CTA per box
+// 5b. boxes: one CTA per box.  The kernel is a sequence of phases, each a __noinline__ function with a handful of scalar
+//     arguments (everything else lives in shared memory): inlined into one body, the pixel loops ran at the 80-register cap
+//     of 3 CTAs per SM with ~50 box-level values live across them, and ptxas rematerialised loop invariants on every
+//     iteration -- 68 SASS instructions per quad in the light pass where ~30 do the work (ncu, profiles/).
 // ------------------------------------------------------------------------------------------
 struct TileBoxShared {
   LargeShared ls;
   double red_d[kBlkWarps][3];
   float red_f[kBlkWarps][6];
-  int red_i[kBlkWarps][4];
+  int red_i[kBlkWarps][5];       // valid pixels (tiles + strips), of the strips, of "all under" tiles, of scanned tiles; over-range flag
   int scan_w[kBlkWarps];
-  int b_lo, b_hi, before, end, ncoll, item, n_scan;
+  int b_lo, b_hi, before, end, ncoll, item, n_scan, ncap;
+  uint32_t sel[2];
+  int sr[4][4], n_sr;            // boundary strips {x0, y0, x1, y1}
+  int tx_lo, ty_lo, ntx_i, n_int;  // completely covered tiles: origin, tiles per row, count
 };
+constexpr int kTileRingWords = LM3D_TILE_SCAN_LDG ? 0 : kBlkThreads * 4 * LM3D_TILE_RING_;
+constexpr int kTileShOff = kTileHistWords + kSortCap + kTileMaxInt + kTileListPad + kTileRingWords;  // word offset of TileBoxShared in dynamic shared memory
+constexpr int kTileBoxSmemWords = kTileShOff + (int)((sizeof(TileBoxShared) + 3) / 4);
+static_assert((kTileShOff * 4) % 16 == 0, "TileBoxShared alignment");
 
-// pass over one sub-rect of the box: MODE 0 = pass 1 (reduce + histogram), MODE 1 = pass 2 (append the keys whose
-// histogram word lies in [tgt, tgt + dt] to sortbuf)
+__device__ __forceinline__ TileBoxShared& tile_sh() {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  return *reinterpret_cast<TileBoxShared*>(smem_u32 + kTileShOff);
+}
+
+// pass over one sub-rect of the box: MODE 0 = pass 1 (reduce + histogram + capture of the in-bracket keys), MODE 1 = pass 2
+// (append the keys whose histogram word lies in [tgt, tgt + dt] to sortbuf)
 template <int MODE>
 __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, int W, int rx0, int ry0, int rx1, int ry1,
                                                uint32_t dmax_bits, const FrameTab& tb, float uc, float vc, float s4f, float kkf,
@@ -238,7 +264,8 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
         if (st + i >= nsteps) break;
         const uint4 q0 = qb[i];
         if (MODE == 0) {
-          accum_quad_hist<false>(q0, dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, 0u, 0u, no_cptr);
+          accum_quad_hist<LM3D_TILE_STRIP_CAPTURE ? 2 : 0>(q0, dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, tgt, dt,
+                                                           no_cptr, sortbuf, ncoll, kTileStripCap);
           vr += frp;
         } else {
           const uint32_t bits[4] = {q0.x, q0.y, q0.z, q0.w};
@@ -267,21 +294,113 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
   }
 }
 
-// light pass over the listed tiles (completely inside the rect and the frame: no masks, no geometry).  The 64 quads of
-// a tile go to 64 consecutive threads, so a thread keeps ONE (row, quad column) position and walks the tiles four
-// apart: a load costs one shared-memory read of the tile's offset and one add.  kTileScanBatch loads in flight.
-// MODE 0: histogram update, MODE 1: collect the keys whose histogram word lies in [tgt, tgt + dt].
+// ---- phase: request the strips' cache lines into L2.  tile_sum_kernel streamed the whole chunk through L2 since, so
+//      the strips come from DRAM; the requests overlap the bracket search.  One per 32 pixels of a strip row + its last pixel.
+__device__ __noinline__ void tile_prefetch_strips(const float* __restrict__ fbase, int W) {
+  const TileBoxShared& sh = tile_sh();
+  const int n_sr = sh.n_sr;
+#pragma unroll 1
+  for (int s = 0; s < n_sr; ++s) {
+    const int x0 = sh.sr[s][0], y0 = sh.sr[s][1], x1 = sh.sr[s][2], y1 = sh.sr[s][3];
+    const int per_row = (x1 - x0 + 32) / 32 + 1, n_req = per_row * (y1 - y0 + 1);
+    for (int i = threadIdx.x; i < n_req; i += kBlkThreads) {
+      const int row = i / per_row, k = i - row * per_row;
+      const float* pp = fbase + (size_t)(y0 + row) * W + min(x0 + 32 * k, x1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+    }
+  }
+}
+
+// ---- phase: everything of pass 1 but the scan of the listed tiles.  Completely covered tiles contribute their TileSum
+//      (and go on the scan list when their depth range straddles the bracket [lo, hi]), the strips are walked pixel by
+//      pixel (reduce + histogram + capture); the per-warp partials go to shared memory. -----------------------------------
+__device__ __noinline__ void tile_pass1_sums(const float* __restrict__ fbase, int W, const TileSum* __restrict__ ts, int ntx_frame,
+                                             const FrameTab* __restrict__ tab_f, uint32_t dmax_bits, uint32_t lo, uint32_t hi,
+                                             float uc, float vc, float s4f, float kkf) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  TileBoxShared& sh = tile_sh();
+  uint32_t* sortbuf = smem_u32 + kTileHistWords;
+  uint32_t* scan_list = sortbuf + kSortCap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t hist_bias = (uint32_t)__cvta_generic_to_shared(smem_u32) - 0x30000000u;
+  const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
+  AccQ acc;
+  acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
+  acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
+  acc.sv = 0.f; acc.n_valid = 0.f;
+  double ds0 = 0.0, dsu = 0.0, dsv = 0.0;
+  int nv_t = 0, below_t = 0, nvs_t = 0, over_t = 0;
+  {
+    const int n_int = sh.n_int, ntx_i = sh.ntx_i, tx_lo = sh.tx_lo, ty_lo = sh.ty_lo;
+    const float dmax_f = __uint_as_float(dmax_bits);
+    for (int i = tid; i < n_int; i += kBlkThreads) {
+      const int iy = i / ntx_i, ix = i - iy * ntx_i;
+      const int tx = tx_lo + ix, ty = ty_lo + iy;
+      const float4* p = reinterpret_cast<const float4*>(ts + (ty * ntx_frame + tx));
+      const float4 a = __ldcg(p), m = __ldcg(p + 1), x = __ldcg(p + 2);
+      const float rawmax = __ldcg(reinterpret_cast<const float*>(p + 3));
+      const int nv = __float_as_int(a.x);
+      if (nv > 0) {
+        nv_t += nv;
+        const double s0 = (double)a.y;
+        ds0 += s0;
+        dsu += (double)a.z + ((double)(tx * kTile) + 7.5 - (double)uc) * s0;
+        dsv += (double)a.w + ((double)(ty * kTile) + 7.5 - (double)vc) * s0;
+        acc.mn0 = fminf(acc.mn0, m.x); acc.mn1 = fminf(acc.mn1, m.y); acc.mn2 = fminf(acc.mn2, m.z);
+        acc.mx0 = fmaxf(acc.mx0, m.w); acc.mx1 = fmaxf(acc.mx1, x.x); acc.mx2 = fmaxf(acc.mx2, x.y);
+        // depth range vs the bracket [lo, hi] (keys): all under -> counted, all over -> nothing, else scanned
+        if (__float_as_uint(x.w) < lo) below_t += nv;
+        else if (__float_as_uint(x.z) <= hi) {
+          scan_list[atomicAdd(&sh.n_scan, 1)] = (uint32_t)((ty * kTile) * W + tx * kTile);
+          nvs_t += nv;
+          over_t |= (rawmax > dmax_f) ? 1 : 0;  // the tile holds a pixel over max_depth (or +inf): the light pass must test validity
+        }
+      }
+    }
+  }
+  float s0_all = 0.f, su = 0.f;
+  {
+    const FrameTab tb = load_tab(tab_f, 0);
+    const int n_sr = sh.n_sr;
+#pragma unroll 1
+    for (int s = 0; s < n_sr; ++s)
+      tile_rect_pass<0>(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
+                        acc, s0_all, su, 0x4C000000u + 256u, (uint32_t)kBlkBins - 1u, sortbuf + kTileCollCap, &sh.ncap);
+  }
+  const int nv_strips_l = (int)acc.n_valid;
+  const double d0 = warp_sum_d(ds0 + (double)s0_all), d1 = warp_sum_d(dsu + (double)su), d2 = warp_sum_d(dsv + (double)acc.sv);
+  const float f0 = warp_min_f(acc.mn0), f1 = warp_min_f(acc.mn1), f2 = warp_min_f(acc.mn2);
+  const float f3 = warp_max_f(acc.mx0), f4 = warp_max_f(acc.mx1), f5 = warp_max_f(acc.mx2);
+  const int i0 = warp_sum_i(nv_t + nv_strips_l), i1 = warp_sum_i(nv_strips_l), i2 = warp_sum_i(below_t), i3 = warp_sum_i(nvs_t);
+  const int i4 = __any_sync(kFull, over_t != 0) ? 1 : 0;
+  if (lane == 0) {
+    sh.red_d[warp][0] = d0; sh.red_d[warp][1] = d1; sh.red_d[warp][2] = d2;
+    sh.red_f[warp][0] = f0; sh.red_f[warp][1] = f1; sh.red_f[warp][2] = f2;
+    sh.red_f[warp][3] = f3; sh.red_f[warp][4] = f4; sh.red_f[warp][5] = f5;
+    sh.red_i[warp][0] = i0; sh.red_i[warp][1] = i1; sh.red_i[warp][2] = i2; sh.red_i[warp][3] = i3; sh.red_i[warp][4] = i4;
+  }
+}
+
+// ---- phase: light pass over the listed tiles (completely inside the rect and the frame: no masks, no geometry).  The 64
+//      quads of a tile go to 64 consecutive threads, so a thread keeps ONE (row, quad column) position and walks the tiles
+//      four apart.  Fed by a cp.async ring: the thread's quad of tile m + kTileRing is requested (LDGSTS, no registers held)
+//      before its quad of tile m is reduced (register-held batches cap the loads in flight at the register budget:
+//      2.82 ms vs 2.27 ms on C3 x 200 frames).
+//      MODE 0: histogram update.  CHECK = false when no listed tile holds an over-range pixel and the map sends every
+//      d <= 0 under the bins: then an invalid pixel (0, negative, NaN) lands in the private "below" words through the clamp
+//      alone, exactly where the validity select would have sent it, and the 12 instructions per quad of the test go.
+//      MODE 1: collect the keys whose histogram word lies in [tgt, tgt + dt] (a packed fma and one branch per quad). -----
 constexpr int kTileRing = LM3D_TILE_RING;
-// what a scan pass does with one quad of a listed tile (MODE 0: histogram update, MODE 1: collect)
-template <int MODE>
-__device__ __forceinline__ void tile_scan_quad(const uint4 q, uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi,
-                                               uint32_t hist_bias, uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
+// what a scan pass does with one quad of a listed tile
+template <int MODE, bool CHECK>
+__device__ __forceinline__ void tile_scan_quad(const uint4 q, uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
+                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
   const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
   float y[4];
   if (MODE == 0) {
     uint32_t key[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) key[j] = key_valid(bits[j], dmax_bits) ? bits[j] : 0x7fffffffu;
+    for (int j = 0; j < 4; ++j) key[j] = (!CHECK || key_valid(bits[j], dmax_bits)) ? bits[j] : 0x7fffffffu;
     unpack2(fma2(pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
     unpack2(fma2(pack2(__uint_as_float(key[2]), __uint_as_float(key[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
 #pragma unroll
@@ -307,91 +426,43 @@ __device__ __forceinline__ void tile_scan_quad(const uint4 q, uint32_t dmax_bits
   }
 }
 
-// TMA feed of the scan passes (LM3D_TILE_FEED = 1): a 64-thread group owns a ring of kTileRing 1 KB tile buffers, each
-// with an mbarrier.  Lane 0 of the group's first warp announces 1024 bytes (arrive.expect_tx), its lanes 0..15 issue
-// one bulk copy each (cp.async.bulk, a 64-byte tile row; SASS UBLKCP) -- 17 instructions per tile instead of 64 LDGSTS
-// with the three inserted LDS each.  The 64 threads wait on the barrier's phase, read their quad, reduce it, meet at
-// the group's named barrier (the buffer is free again) and the producer lanes refill it with the tile kTileRing ahead.
-__device__ __forceinline__ void bulk_copy_64(uint32_t dst_s, const void* src, uint32_t bar_s) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];" ::"r"(dst_s), "l"(src),
-               "r"(bar_s)
-               : "memory");
-}
-constexpr int kTileStage = LM3D_TILE_STAGE, kTileTmaRing = LM3D_TILE_TMA_RING;
-template <int MODE>
-__device__ __forceinline__ void tile_scan_pass_tma(const float* __restrict__ fbase, int W, const uint32_t* scan_list, int n_scan,
-                                                   uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
-                                                   uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll, uint32_t ring_base_s,
-                                                   uint32_t bar_base_s, uint32_t& phase, const void* tmap, int frame) {
-  const int g = threadIdx.x >> 6, t64 = threadIdx.x & 63, lane = threadIdx.x & 31;
-  const bool producer_warp = (threadIdx.x & 32) == 0;
-  const int n_my = (n_scan - g + 3) >> 2;                     // tiles g, g + 4, ... (same for the 64 threads of the group)
-  const int n_st = (n_my + kTileStage - 1) / kTileStage;      // stages of kTileStage tiles
-  constexpr uint32_t kStageBytes = kTileStage * 1024u;
-  const uint32_t buf0 = ring_base_s + (uint32_t)(g * kTileTmaRing) * kStageBytes, bar0 = bar_base_s + (uint32_t)(g * kTileTmaRing) * 8u;
-  auto issue = [&](int st, int i) {
-    const int m0 = st * kTileStage, cnt = min(kTileStage, n_my - m0);
-#if LM3D_TILE_FEED == 2
-    // one tensor-map request per tile: cp.async.bulk.tensor.3d, box 16 x 16 x 1 of depth[F,H,W] (SASS UTMALDG)
-    if (producer_warp) {
-      if (lane == 0) mbar_expect_tx(bar0 + i * 8, 1024u * (uint32_t)cnt);
-      __syncwarp();
-      if (lane < cnt) {
-        const uint32_t off = scan_list[g + 4 * (m0 + lane)];  // (ty * 16) * W + tx * 16
-        const int row = (int)(off / (uint32_t)W);
-        tma_load_tile_3d(buf0 + i * kStageBytes + lane * 1024, tmap, bar0 + i * 8, (int)off - row * W, row, frame);
-      }
-    }
-#else
-    if (producer_warp) {
-      if (lane == 0) mbar_expect_tx(bar0 + i * 8, 1024u * (uint32_t)cnt);
-      __syncwarp();
-      for (int k = 0; k < cnt; ++k)
-        if (lane < 16) bulk_copy_64(buf0 + i * kStageBytes + k * 1024 + lane * 64, fbase + scan_list[g + 4 * (m0 + k)] + lane * W, bar0 + i * 8);
-    }
-#endif
-  };
+template <int MODE, bool CHECK>
+__device__ __noinline__ void tile_scan_pass(const float* __restrict__ fbase, int W, int n_scan, uint32_t dmax_bits, float s4f, float kkf,
+                                            uint32_t tgt, uint32_t dt) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int tid = threadIdx.x;
+  uint32_t* sortbuf = smem_u32 + kTileHistWords;
+  const uint32_t* scan_list = sortbuf + kSortCap + (tid >> 6);      // the 64-thread group takes tiles g, g + 4, g + 8, ...
+  int* ncoll = &tile_sh().ncoll;
+  const uint32_t hist_bias = (uint32_t)__cvta_generic_to_shared(smem_u32) - 0x30000000u;
+  const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
+  const float* __restrict__ qp = fbase + (((tid & 63) >> 2) * W + (tid & 3) * 4);  // (row, quad column) inside a tile
+  const int n_my = (n_scan - (tid >> 6) + 3) >> 2;     // (same for the 64 threads of a group: warp-uniform control)
+  // (the list is padded with kTileListPad zero offsets: requests past the end read the frame's first tile and are dropped)
+#if LM3D_TILE_SCAN_LDG
+  uint4 qa[4], qb[4];
 #pragma unroll
-  for (int i = 0; i < kTileTmaRing; ++i)
-    if (i < n_st) issue(i, i);
+  for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * i]);
 #pragma unroll 1
-  for (int s0 = 0; s0 < n_st; s0 += kTileTmaRing) {
+  for (int m0 = 0; m0 < n_my; m0 += 8) {
 #pragma unroll
-    for (int i = 0; i < kTileTmaRing; ++i) {
-      const int st = s0 + i;
-      if (st >= n_st) break;
-      mbar_wait(bar0 + i * 8, (phase >> i) & 1u);
-      phase ^= 1u << i;
-      const int cnt = min(kTileStage, n_my - st * kTileStage);
+    for (int i = 0; i < 4; ++i) qb[i] = ldg_u4(qp + scan_list[4 * (m0 + 4 + i)]);
 #pragma unroll
-      for (int k = 0; k < kTileStage; ++k)
-        if (k < cnt) tile_scan_quad<MODE>(lds_u4(buf0 + i * kStageBytes + k * 1024 + t64 * 16), dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
-      // every thread of the group has consumed stage i (named barriers 1..4: constant ids keep the CTA at 5 barriers)
-      if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-      else if (g == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
-      else if (g == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
-      else asm volatile("bar.sync 4, 64;" ::: "memory");
-      if (st + kTileTmaRing < n_st) issue(st + kTileTmaRing, i);
-    }
+    for (int i = 0; i < 4; ++i)
+      if (m0 + i < n_my) tile_scan_quad<MODE, CHECK>(qa[i], dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
+    if (m0 + 4 >= n_my) break;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * (m0 + 8 + i)]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (m0 + 4 + i < n_my) tile_scan_quad<MODE, CHECK>(qb[i], dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
   }
-}
-
-template <int MODE>
-__device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, int W, const uint32_t* scan_list, int n_scan,
-                                               uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
-                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll, uint32_t ring_s) {
-  // cp.async ring: the thread's quad of tile m + kTileRing is requested (LDGSTS, no registers held) before its quad
-  // of tile m is reduced -- eight 16-byte loads in flight per thread.  The kernel is bound by load latency (ncu: a
-  // third of the issue slots used, long-scoreboard the top stall) and register-held batches cap the loads in
-  // flight at the register budget; the ring does not.  Measured on C3 x 200 frames: 2.82 ms with register batches of 4, 2.27 ms with the ring.
-  const float* __restrict__ qp = fbase + (((threadIdx.x & 63) >> 2) * W + (threadIdx.x & 3) * 4);  // (row, quad column) inside a tile
-  const int g = threadIdx.x >> 6;                      // the 64-thread group takes tiles g, g + 4, g + 8, ...
-  const int n_my = (n_scan - g + 3) >> 2;              // (same for the 64 threads of a group: warp-uniform control)
+#else
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem_u32 + kTileHistWords + kSortCap + kTileMaxInt + kTileListPad) + (uint32_t)tid * 16;
   constexpr uint32_t kSlot = kBlkThreads * 16;
 #pragma unroll
   for (int i = 0; i < kTileRing; ++i) {
-    const bool ok = i < n_my;
-    cp_async_16(ring_s + i * kSlot, qp + (ok ? scan_list[g + 4 * i] : 0u), ok ? 16u : 0u);
+    cp_async_16(ring_s + i * kSlot, qp + scan_list[4 * i], 16u);
     cp_async_commit();
   }
 #pragma unroll 1
@@ -402,16 +473,46 @@ __device__ __forceinline__ void tile_scan_pass(const float* __restrict__ fbase, 
       if (m >= n_my) break;
       cp_async_wait<kTileRing - 1>();
       const uint4 q = lds_u4(ring_s + i * kSlot);
-      {
-        const int mn = m + kTileRing;
-        const bool ok = mn < n_my;
-        cp_async_16(ring_s + i * kSlot, qp + (ok ? scan_list[g + 4 * mn] : 0u), ok ? 16u : 0u);
-        cp_async_commit();
-      }
-      tile_scan_quad<MODE>(q, dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
+      cp_async_16(ring_s + i * kSlot, qp + scan_list[4 * (m + kTileRing)], 16u);
+      cp_async_commit();
+      tile_scan_quad<MODE, CHECK>(q, dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
     }
   }
-  cp_async_wait<0>();  // drain the (zero-size) requests past the end before the slots are reused
+  cp_async_wait<0>();  // drain the requests past the end before the slots are reused
+#endif
+}
+
+// ---- phase: pass 2 over the strips.  Their keys that fell into a bracket bin were captured by pass 1; when the capture
+//      buffer overflowed (a box whose strips hold thousands of in-bracket keys) the strips are walked again. -----------------
+__device__ __noinline__ void tile_strips_pass2(const float* __restrict__ fbase, int W, uint32_t dmax_bits, float s4f, float kkf, uint32_t tgt,
+                                               uint32_t dt) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  TileBoxShared& sh = tile_sh();
+  uint32_t* sortbuf = smem_u32 + kTileHistWords;
+#if LM3D_TILE_STRIP_CAPTURE
+  const int ncap = sh.ncap;
+  if (ncap <= kTileStripCap) {
+    const uint32_t* capbuf = sortbuf + kTileCollCap;
+    for (int i = threadIdx.x; i < ncap; i += kBlkThreads) {
+      const uint32_t key = capbuf[i];
+      if (__float_as_uint(fmaf(__uint_as_float(key), s4f, kkf)) - tgt <= dt) {
+        const int pos = atomicAdd(&sh.ncoll, 1);
+        if (pos < kTileCollCap) sortbuf[pos] = key;
+      }
+    }
+    return;
+  }
+#endif
+  FrameTab tb;  // (not read by MODE 1)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) tb.a[k] = tb.b[k] = tb.c[k] = tb.t[k] = 0.f;
+  AccQ acc;
+  float d0 = 0.f, d1 = 0.f;
+  const int n_sr = sh.n_sr;
+#pragma unroll 1
+  for (int s = 0; s < n_sr; ++s)
+    tile_rect_pass<1>(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], dmax_bits, tb, 0.f, 0.f, s4f, kkf, 0.f, 0.f, 0u, acc, d0, d1,
+                      tgt, dt, sortbuf, &sh.ncoll);
 }
 
 // LM3D_TILE_TIMING (dev builds only): thread 0 of every CTA adds the clock64() cycles of each phase of a box to
@@ -423,26 +524,15 @@ __device__ unsigned long long g_tile_prof[16];
 #define TILE_T(ph) do { } while (0)
 #endif
 #ifndef LM3D_TILE_MINB
-#define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers (32 bytes of spills) beats 2 CTAs at 124 and 4 at 64 (C3 x 200: 2.27 / 2.41 / 2.41 ms)
+#define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers beats 2 CTAs at 124 and 4 at 64 (C3 x 200: 2.27 / 2.41 / 2.41 ms)
 #endif
-__global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* hist = smem_u32;                           // [256 | kBlkBins | 256] as in lift_block_kernel
-  uint32_t* sortbuf = smem_u32 + kTileHistWords;       // [kSortCap]: lattice sample, then the collected keys
-  uint32_t* scan_list = sortbuf + kSortCap;            // [kTileMaxInt]: pixel offset of the tiles to scan
-  __shared__ TileBoxShared sh;
+  uint32_t* sortbuf = smem_u32 + kTileHistWords;       // [kSortCap]: [0, 2048) the collected keys, [2048, 4096) the strips' capture
+  TileBoxShared& sh = tile_sh();
   const LiftArgs& A = T.A;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-  [[maybe_unused]] const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(scan_list + kTileMaxInt + 16) + (uint32_t)tid * 16;
-  [[maybe_unused]] const uint32_t ring_base_s = ((uint32_t)__cvta_generic_to_shared(scan_list + kTileMaxInt + 16) + 127u) & ~127u;  // (TMA tiles land 128-byte aligned)
-  [[maybe_unused]] const uint32_t bar_base_s = ring_base_s + 4u * kTileTmaRing * kTileStage * 1024u;  // 4 groups x kTileTmaRing mbarriers (8 bytes each)
-  [[maybe_unused]] uint32_t tma_phase = 0u;  // parity of every ring barrier (a bit per stage), carried across passes and boxes
-#if LM3D_TILE_FEED
-  if (tid < 4 * kTileTmaRing) mbar_init(bar_base_s + tid * 8, 1);
-  mbar_fence_init();
-  __syncthreads();
-#endif
   const int W = A.W, H = A.H;
   const int n_tiles = T.ntx * T.nty;
   const int b_begin = (int)T.frame_off[T.f0], b_end = (int)T.frame_off[T.f0 + T.nf];
@@ -464,8 +554,34 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     if (T.frame_area[f] < T.area_thr) continue;              // frame under the cover threshold: lift_block_kernel has it
     const int slot = f - T.f0;
     const float* __restrict__ fbase = A.depth + (size_t)f * H * W;
-    const FrameTab tb = load_tab(A.tab, f);
     const float uc = 0.5f * (float)(rc.x0 + rc.x1), vc = 0.5f * (float)(rc.y0 + rc.y1);
+
+    // ---- tiles completely inside the rect; the rest of the rect = up to four strips -----------------------------
+    if (tid == 0) {
+      const int tx_lo = (rc.x0 + kTile - 1) / kTile, tx_hi = min((rc.x1 + 1) / kTile, T.ntx) - 1;
+      const int ty_lo = (rc.y0 + kTile - 1) / kTile, ty_hi = min((rc.y1 + 1) / kTile, T.nty) - 1;
+      const bool has_int = tx_lo <= tx_hi && ty_lo <= ty_hi && (tx_hi - tx_lo + 1) * (ty_hi - ty_lo + 1) <= kTileMaxInt;
+      const int ntx_i = has_int ? tx_hi - tx_lo + 1 : 0, nty_i = has_int ? ty_hi - ty_lo + 1 : 0;
+      sh.tx_lo = tx_lo; sh.ty_lo = ty_lo; sh.ntx_i = ntx_i; sh.n_int = ntx_i * nty_i;
+      int n_sr = 0;
+      auto strip = [&](int x0, int y0, int x1, int y1) { sh.sr[n_sr][0] = x0; sh.sr[n_sr][1] = y0; sh.sr[n_sr][2] = x1; sh.sr[n_sr][3] = y1; ++n_sr; };
+      if (!has_int) {
+        strip(rc.x0, rc.y0, rc.x1, rc.y1);
+      } else {
+        const int iy0 = ty_lo * kTile, iy1 = (ty_hi + 1) * kTile - 1;
+        const int ix0 = tx_lo * kTile, ix1 = (tx_hi + 1) * kTile - 1;
+        if (rc.y0 < iy0) strip(rc.x0, rc.y0, rc.x1, iy0 - 1);
+        if (iy1 < rc.y1) strip(rc.x0, iy1 + 1, rc.x1, rc.y1);
+        if (rc.x0 < ix0) strip(rc.x0, iy0, ix0 - 1, iy1);
+        if (ix1 < rc.x1) strip(ix1 + 1, iy0, rc.x1, iy1);
+      }
+      sh.n_sr = n_sr;
+      sh.n_scan = 0; sh.ncoll = 0; sh.ncap = 0;
+    }
+    __syncthreads();
+#if LM3D_TILE_PREFETCH
+    tile_prefetch_strips(fbase, W);
+#endif
     TILE_T(0);
 
     // ---- lattice sample -> bracket [lo, hi] in key space (binned, no sort: block_bracket_binned) --------------------
@@ -477,97 +593,29 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     const float wd = whi_f - wlo_f;
     const float s4f = (wd > 0.f) ? fminf(4000.f / wd, 2097152.f / whi_f) : 0.f;  // 1000 bins x 4
     const float kkf = fmaf(-wlo_f, s4f, 33554432.f + 4.f * 268.f);               // window low edge -> word 268
-    const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
-    const uint32_t hist_bias = hist_s - 0x30000000u;
     __syncthreads();
     for (int i = tid; i < kTileHistWords; i += kBlkThreads) hist[i] = 0u;
-    if (tid == 0) { sh.n_scan = 0; sh.ncoll = 0; }
     __syncthreads();
 
-    // ---- tiles completely inside the rect; the rest of the rect = up to four strips -----------------------------
-    const int tx_lo = (rc.x0 + kTile - 1) / kTile, tx_hi = min((rc.x1 + 1) / kTile, T.ntx) - 1;
-    const int ty_lo = (rc.y0 + kTile - 1) / kTile, ty_hi = min((rc.y1 + 1) / kTile, T.nty) - 1;
-    const bool has_int = tx_lo <= tx_hi && ty_lo <= ty_hi && (tx_hi - tx_lo + 1) * (ty_hi - ty_lo + 1) <= kTileMaxInt;
-    const int ntx_i = has_int ? tx_hi - tx_lo + 1 : 0, nty_i = has_int ? ty_hi - ty_lo + 1 : 0;
-    const int n_int = ntx_i * nty_i;
-    int sr[4][4];
-    int n_sr = 0;
-    if (!has_int) {
-      sr[0][0] = rc.x0; sr[0][1] = rc.y0; sr[0][2] = rc.x1; sr[0][3] = rc.y1; n_sr = 1;
-    } else {
-      const int iy0 = ty_lo * kTile, iy1 = (ty_hi + 1) * kTile - 1;
-      const int ix0 = tx_lo * kTile, ix1 = (tx_hi + 1) * kTile - 1;
-      if (rc.y0 < iy0) { sr[n_sr][0] = rc.x0; sr[n_sr][1] = rc.y0; sr[n_sr][2] = rc.x1; sr[n_sr][3] = iy0 - 1; ++n_sr; }
-      if (iy1 < rc.y1) { sr[n_sr][0] = rc.x0; sr[n_sr][1] = iy1 + 1; sr[n_sr][2] = rc.x1; sr[n_sr][3] = rc.y1; ++n_sr; }
-      if (rc.x0 < ix0) { sr[n_sr][0] = rc.x0; sr[n_sr][1] = iy0; sr[n_sr][2] = ix0 - 1; sr[n_sr][3] = iy1; ++n_sr; }
-      if (ix1 < rc.x1) { sr[n_sr][0] = ix1 + 1; sr[n_sr][1] = iy0; sr[n_sr][2] = rc.x1; sr[n_sr][3] = iy1; ++n_sr; }
-    }
-
-    // ---- interior tiles: summaries; the tiles whose depth range straddles the bracket go on the scan list ----------
-    AccQ acc;
-    acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
-    acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
-    acc.sv = 0.f; acc.n_valid = 0.f;
-    double ds0 = 0.0, dsu = 0.0, dsv = 0.0;
-    int nv_t = 0, below_t = 0, nvs_t = 0;
-    if (has_int) {
-      const TileSum* ts = T.tsum + (size_t)slot * n_tiles;
-      for (int i = tid; i < n_int; i += kBlkThreads) {
-        const int iy = i / ntx_i, ix = i - iy * ntx_i;
-        const int tx = tx_lo + ix, ty = ty_lo + iy;
-        const float4* p = reinterpret_cast<const float4*>(ts + (ty * T.ntx + tx));
-        const float4 a = __ldcg(p), m = __ldcg(p + 1), x = __ldcg(p + 2);
-        const int nv = __float_as_int(a.x);
-        if (nv > 0) {
-          nv_t += nv;
-          const double s0 = (double)a.y;
-          ds0 += s0;
-          dsu += (double)a.z + ((double)(tx * kTile) + 7.5 - (double)uc) * s0;
-          dsv += (double)a.w + ((double)(ty * kTile) + 7.5 - (double)vc) * s0;
-          acc.mn0 = fminf(acc.mn0, m.x); acc.mn1 = fminf(acc.mn1, m.y); acc.mn2 = fminf(acc.mn2, m.z);
-          acc.mx0 = fmaxf(acc.mx0, m.w); acc.mx1 = fmaxf(acc.mx1, x.x); acc.mx2 = fmaxf(acc.mx2, x.y);
-          // depth range vs the bracket [lo, hi] (keys): all under -> counted, all over -> nothing, else scanned
-          if (__float_as_uint(x.w) < lo) below_t += nv;
-          else if (__float_as_uint(x.z) <= hi) { scan_list[atomicAdd(&sh.n_scan, 1)] = (uint32_t)((ty * kTile) * W + tx * kTile); nvs_t += nv; }
-        }
-      }
-    }
-
-    TILE_T(2);
-    // ---- pass 1: strips pixel by pixel, listed tiles with the light pass -----------------------------------------
-    float s0_all = 0.f, su = 0.f;
-    for (int s = 0; s < n_sr; ++s)
-      tile_rect_pass<0>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
-                        acc, s0_all, su, 0u, 0u, nullptr, nullptr);
-    const int nv_strips_l = (int)acc.n_valid;
+    // ---- pass 1: tile summaries + strips, then the light pass over the listed tiles -----------------------------
+    tile_pass1_sums(fbase, W, T.tsum + (size_t)slot * n_tiles, T.ntx, A.tab + f, A.dmax_bits, lo, hi, uc, vc, s4f, kkf);
     __syncthreads();
     TILE_T(3);
     const int n_scan = sh.n_scan;
-#if LM3D_TILE_FEED
-    tile_scan_pass_tma<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_base_s, bar_base_s, tma_phase, &tmap, f);
-#else
-    tile_scan_pass<0>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, 0u, 0u, nullptr, nullptr, ring_s);
-#endif
-
-#ifdef LM3D_TILE_TIMING
+    if (tid < kTileListPad) sortbuf[kSortCap + n_scan + tid] = 0u;  // pad the scan list for the ring's requests past its end
     __syncthreads();
-#endif
-    TILE_T(4);
-    // ---- block reduction -----------------------------------------------------------------------------------
     {
-      const double d0 = warp_sum_d(ds0 + (double)s0_all), d1 = warp_sum_d(dsu + (double)su), d2 = warp_sum_d(dsv + (double)acc.sv);
-      const float f0 = warp_min_f(acc.mn0), f1 = warp_min_f(acc.mn1), f2 = warp_min_f(acc.mn2);
-      const float f3 = warp_max_f(acc.mx0), f4 = warp_max_f(acc.mx1), f5 = warp_max_f(acc.mx2);
-      const int i0 = warp_sum_i(nv_t + nv_strips_l), i1 = warp_sum_i(nv_strips_l), i2 = warp_sum_i(below_t), i3 = warp_sum_i(nvs_t);
-      __syncthreads();
-      if (lane == 0) {
-        sh.red_d[warp][0] = d0; sh.red_d[warp][1] = d1; sh.red_d[warp][2] = d2;
-        sh.red_f[warp][0] = f0; sh.red_f[warp][1] = f1; sh.red_f[warp][2] = f2;
-        sh.red_f[warp][3] = f3; sh.red_f[warp][4] = f4; sh.red_f[warp][5] = f5;
-        sh.red_i[warp][0] = i0; sh.red_i[warp][1] = i1; sh.red_i[warp][2] = i2; sh.red_i[warp][3] = i3;
-      }
-      __syncthreads();
+      int over = 0;
+#pragma unroll
+      for (int w = 0; w < kBlkWarps; ++w) over |= sh.red_i[w][4];
+      // the clamp alone sorts invalid pixels iff every d <= 0 maps under the bins (kkf = the image of 0) and nothing listed is over range
+      if (over || !(kkf < 33554432.f + 4.f * 256.f)) tile_scan_pass<0, true>(fbase, W, n_scan, A.dmax_bits, s4f, kkf, 0u, 0u);
+      else tile_scan_pass<0, false>(fbase, W, n_scan, A.dmax_bits, s4f, kkf, 0u, 0u);
     }
+    __syncthreads();
+    TILE_T(4);
+
+    // ---- block reduction of the per-warp partials ---------------------------------------------------------------
     BoxSums S;
     S.s0 = S.su = S.sv = 0.0;
     S.n_valid = 0;
@@ -635,33 +683,41 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       } else {
         const uint32_t tgt = 0x4C000000u + (uint32_t)b_lo, dt = (uint32_t)(b_hi - b_lo);
         TILE_T(5);
-        float d0 = 0.f, d1 = 0.f;
-        for (int s = 0; s < n_sr; ++s)
-          tile_rect_pass<1>(fbase, W, sr[s][0], sr[s][1], sr[s][2], sr[s][3], A.dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
-                            acc, d0, d1, tgt, dt, sortbuf, &sh.ncoll);
+        tile_strips_pass2(fbase, W, A.dmax_bits, s4f, kkf, tgt, dt);
 #ifdef LM3D_TILE_TIMING
         __syncthreads();
 #endif
         TILE_T(6);
-#if LM3D_TILE_FEED
-        tile_scan_pass_tma<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_base_s, bar_base_s, tma_phase, &tmap, f);
-#else
-        tile_scan_pass<1>(fbase, W, scan_list, n_scan, A.dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, &sh.ncoll, ring_s);
-#endif
+        tile_scan_pass<1, true>(fbase, W, n_scan, A.dmax_bits, s4f, kkf, tgt, dt);
         __syncthreads();
         TILE_T(7);
         if (sh.ncoll != n_coll) {
           handover = true;  // (cannot happen: both passes evaluate the same map)
           if (tid == 0) atomicAdd(&A.counters[15], 1);
         } else {
-          int np2 = 32;
-          while (np2 < n_coll) np2 <<= 1;
-          for (int i = n_coll + tid; i < np2; i += kBlkThreads) sortbuf[i] = kKeyInvalid;
-          block_bitonic(sortbuf, np2);
           const int rl = r - before;
-          k0 = sortbuf[rl];
-          k1 = two ? sortbuf[rl + 1] : k0;
-          __syncthreads();
+          if (n_coll <= kBlkThreads) {
+            // a thread per key: its rank = keys under it, its multiplicity = keys equal to it (broadcast reads, one barrier
+            // instead of the ~30 of a bitonic sort of 64-256 keys)
+            if (tid < n_coll) {
+              const uint32_t key = sortbuf[tid];
+              int less = 0, eq = 0;
+              for (int i = 0; i < n_coll; ++i) { const uint32_t o = sortbuf[i]; less += (o < key); eq += (o == key); }
+              if (less <= rl && rl < less + eq) sh.sel[0] = key;
+              if (less <= rl + 1 && rl + 1 < less + eq) sh.sel[1] = key;
+            }
+            __syncthreads();
+            k0 = sh.sel[0];
+            k1 = two ? sh.sel[1] : k0;
+          } else {
+            int np2 = 512;
+            while (np2 < n_coll) np2 <<= 1;
+            for (int i = n_coll + tid; i < np2; i += kBlkThreads) sortbuf[i] = kKeyInvalid;
+            block_bitonic(sortbuf, np2);
+            k0 = sortbuf[rl];
+            k1 = two ? sortbuf[rl + 1] : k0;
+            __syncthreads();
+          }
         }
       }
     }
@@ -674,6 +730,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       continue;
     }
     if (tid == 0) {
+      const FrameTab tb = load_tab(A.tab, f);
       write_record(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr, tb,
                    rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S, k0, k1, gamma, A.scale_depth);
       push_record(A, b);
