@@ -5,55 +5,55 @@
 // three sums, a histogram update, and a second visit for the percentile -- for every pixel of every box: 3.1x (C3)
 // to 16.3x (C5) per frame pixel.  Here the box-independent part of that work is done ONCE per frame pixel:
 //
-//   tile_sum_kernel   per 16 x 16 tile (a warp per 32 x 32 block): count, sums, per-axis world min / max and the
-//                     smallest / largest valid depth of the tile -> TileSum (64 B per 1 KB of pixels).  Registers
+//   tile_sum_kernel   per 16 x 16 tile (a thread per tile): count, sums, per-axis world min / max, the smallest / largest
+//                     valid depth and the largest raw value of the tile -> TileSum (64 B per 1 KB of pixels).  Registers
 //                     only: no shared memory, no atomics.
-//   tile_box_kernel   per box (one CTA), the scheme of lift_block_kernel with the interior taken from the tiles:
-//                       * boundary strips (the part of the rect outside completely covered tiles, < 16 px wide) are
-//                         walked pixel by pixel as before;
-//                       * a completely covered tile contributes its sums / min / max / count from its TileSum;
-//                       * for the percentile, a tile whose depth range lies entirely under (over) the box's
-//                         bracket is counted (ignored) without touching its pixels; only tiles that straddle
-//                         the bracket are scanned, with a light pass (validity + histogram update, 7 instructions
-//                         per pixel instead of 23) and, for the second pass, one compare per pixel.
-//                     On the C3 / C5 law (a flat sign patch in front of a tilted plane) the scanned tiles are the
-//                     patch, ~40 % of a box.
+//   tile_box_kernel   per box (one CTA):
+//                       * a 2048-pixel lattice sample gives a COARSE bracket [lo, hi] (keys) around the target rank;
+//                       * a completely covered tile contributes its sums / min / max / count from its TileSum; its depth
+//                         range decides the rest: entirely under the bracket -> its count goes to "below", entirely over
+//                         -> nothing, straddling -> on the scan list;
+//                       * boundary strips (the part of the rect outside completely covered tiles, < 16 px wide) are walked
+//                         pixel by pixel ONCE: reduce, count the keys under lo, capture the keys inside [lo, hi];
+//                       * pass A: a quarter of the pixels of every listed tile (4 of its 16 rows) goes through the bracket
+//                         histogram (1000 bins across [lo, hi]); the scaled counts give a NARROW bracket [lo', hi'] around
+//                         the rank -- +-3.5 sigma of the sampling error: ~1500 keys of a 173 k-pixel box;
+//                       * pass B: every pixel of the listed tiles, in key space and without any shared-memory traffic but
+//                         the rare hits: count the valid keys under lo' (one subtract, one compare, one predicated add per
+//                         pixel), append the keys inside [lo', hi'] to the collect buffer; the captured strip keys likewise;
+//                       * the order statistics are selected from the collected keys (rank select on <= 256 keys, a key-space
+//                         histogram round in front of it for more).
+//                     On the C3 / C5 law (a flat sign patch in front of a tilted plane) the listed tiles are the patch,
+//                     ~40 % of a box.
 //
-// Exactness: identical to lift_block_kernel -- the bracket histogram is the same monotone fp32 map evaluated by the
-// same fma in both passes, the selected order statistics are bit-exact.  A box whose bracket misses the rank or whose
-// target bins overflow the collect buffer is appended to the CTA-per-box list and finished by lift_block_kernel.
+// Exactness: the brackets only steer which keys are looked at.  Pass B counts every valid key of the listed tiles under
+// lo' and collects every key in [lo', hi'] exactly (integer compares on the raw bit patterns: 0, negatives, NaN, inf and
+// over-range values fall outside both tests); tiles that were not listed lie entirely under lo <= lo' or over hi >= hi'; the
+// strips were counted / captured in the same key space.  A box whose narrow bracket misses the rank (or whose ties overflow
+// a buffer) is appended to the CTA-per-box list and finished by lift_block_kernel.
 //
-// (Round 2 first built a heavier pyramid -- a per-frame bin map, per-tile 256-bin prefix histograms and bin-sorted
-// copies of every tile, so that a box could read its percentile bins off the tiles.  It was exact and parity-green
-// but no faster than one CTA per box: building it cost 65 instructions per frame pixel, and the flat sign patches
-// put tens of thousands of keys into one or two bins, which then had to be streamed again per box.  DESIGN.md 4.4.)
+// (Earlier versions of this round, all parity-green, in DESIGN.md 4.4: a per-frame bin map + per-tile prefix histograms +
+// bin-sorted tile copies; a full-histogram pass 1 + a collect pass 2 over the listed tiles -- bound by the L1 / shared-memory
+// data pipe, 15 wavefronts per quad --; cp.async-ring and TMA feeds for the scan passes.)
 #ifndef LM3D_LIFT_TILES_CUH_
 #define LM3D_LIFT_TILES_CUH_
 
 namespace lm3d {
 
-#ifndef LM3D_TILE_RING
-#define LM3D_TILE_RING 4   // cp.async slots per thread in the scan passes
-#endif
-#define LM3D_TILE_RING_DEF LM3D_TILE_RING
 constexpr int kTile = 16;                    // tile edge in pixels
 constexpr int kTileQuads = kTile * kTile / 4;  // float4 quads per tile (64)
 #ifndef LM3D_TILE_MAXINT
 #define LM3D_TILE_MAXINT 4096
 #endif
 constexpr int kTileMaxInt = LM3D_TILE_MAXINT;  // completely covered tiles per box the scan list holds
-#ifndef LM3D_TILE_SCAN_LDG
-#define LM3D_TILE_SCAN_LDG 1   // scan-pass feed: 1 = LDG.128 into two register batches of four quads (ping-pong), 0 = cp.async ring through shared
-                               // memory.  The L1 data pipe is the kernel's busiest unit (ncu: 62 % of peak, 77 % max): the ring costs a quad
-                               // 4 wavefronts for the LDGSTS store + 4 for the LDS.128 on top of the 4 of the global load
+constexpr int kTileListPad = 32;             // zero offsets behind the list: the batched loads may run past its end
+constexpr int kTileColRows = 40;             // collect columns: rows of 256 words (a thread appends its hits to its own column)
+constexpr int kTileStripCap = 24 * 256;      // strip keys inside the coarse bracket pass 1 may capture (the capture buffer underlies the columns)
+constexpr int kTileStride = 4;               // pass A looks at one pixel row in four of every listed tile
+#ifndef LM3D_TILE_NARROW_Z
+#define LM3D_TILE_NARROW_Z 3.5f
 #endif
-constexpr int kTileListPad = (4 * LM3D_TILE_RING_DEF > 32) ? 4 * LM3D_TILE_RING_DEF : 32;  // zero offsets behind the list for requests past its end
-constexpr int kTileCollCap = 2048;           // keys of the target bins a box may collect (sortbuf[0, 2048))
-constexpr int kTileStripCap = kSortCap - kTileCollCap;  // in-bracket strip keys pass 1 may capture (sortbuf[2048, 4096))
-#ifndef LM3D_TILE_STRIP_CAPTURE
-#define LM3D_TILE_STRIP_CAPTURE 1  // 1: the strips' pass 1 appends the keys that fall into ANY bracket bin to a capture buffer and pass 2 reads
-                                   // that buffer instead of walking the strips again (falls back to the walk when the buffer overflows)
-#endif
+constexpr float kTileNarrowZ = LM3D_TILE_NARROW_Z;  // half-width of the narrow bracket in sigmas of pass A's sampling error
 #ifndef LM3D_TILE_PREFETCH
 #define LM3D_TILE_PREFETCH 1       // 1: the strips' cache lines are requested into L2 (prefetch.global.L2) while the bracket is being found
 #endif
@@ -64,19 +64,12 @@ constexpr int kTileSample = LM3D_TILE_SAMPLE;  // lattice sample per box
 #ifndef LM3D_TILE_BRACKET_Z
 #define LM3D_TILE_BRACKET_Z 3.0f
 #endif
-constexpr float kTileBracketZ = LM3D_TILE_BRACKET_Z;  // bracket half-width in sample sigmas: a miss costs a hand-over to lift_block_kernel
+constexpr float kTileBracketZ = LM3D_TILE_BRACKET_Z;  // coarse bracket half-width in sample sigmas
 #ifndef LM3D_TILE_BATCH
 #define LM3D_TILE_BATCH 4
 #endif
-constexpr int kTileBatch = LM3D_TILE_BATCH;    // loads a thread issues together (strip row steps, tile quads)
-#ifndef LM3D_TILE_RING
-#define LM3D_TILE_RING 4   // cp.async slots per thread in the scan passes (measured on C3 / C5: 4 with 3 CTAs per SM beats 2, 8, 16 and 2 CTAs)
-#endif
-#define LM3D_TILE_RING_ LM3D_TILE_RING
+constexpr int kTileBatch = LM3D_TILE_BATCH;    // loads a thread issues together on the strips
 constexpr int kTileHistWords = 256 + kBlkBins + 256;
-// (Round 2 also measured TMA feeds for the scan passes -- 64-byte bulk rows and 16 x 16 x 1 tensor tiles into an mbarrier ring per
-// 64-thread group: 4.71 ms and 2.74 ms on C3 x 200 frames against 2.16 ms for the ring; a tile is 4 pixels per thread, so the
-// barrier wait + group barrier per stage cost more than the 64 LDGSTS they replace.  Removed; git history has them.)
 
 struct __align__(16) TileSum {   // 64 bytes
   int32_t n_valid;
@@ -190,15 +183,19 @@ struct TileBoxShared {
   LargeShared ls;
   double red_d[kBlkWarps][3];
   float red_f[kBlkWarps][6];
-  int red_i[kBlkWarps][5];       // valid pixels (tiles + strips), of the strips, of "all under" tiles, of scanned tiles; over-range flag
+  int red_i[kBlkWarps][6];       // valid pixels (tiles + strips), of the strips, of "all under" tiles, of listed tiles; over-range flag; strip keys under lo
+  int red_b[kBlkWarps];          // pass B: keys under lo'
   int scan_w[kBlkWarps];
-  int b_lo, b_hi, before, end, ncoll, item, n_scan, ncap;
+  int b_lo, b_hi, before, end, ncoll, item, n_scan, ncap, nsmall;
   uint32_t sel[2];
   int sr[4][4], n_sr;            // boundary strips {x0, y0, x1, y1}
   int tx_lo, ty_lo, ntx_i, n_int;  // completely covered tiles: origin, tiles per row, count
 };
-constexpr int kTileRingWords = LM3D_TILE_SCAN_LDG ? 0 : kBlkThreads * 4 * LM3D_TILE_RING_;
-constexpr int kTileShOff = kTileHistWords + kSortCap + kTileMaxInt + kTileListPad + kTileRingWords;  // word offset of TileBoxShared in dynamic shared memory
+// dynamic shared memory (words): histogram | collect columns (first: strip capture) | scan list (+ pad) | TileBoxShared
+constexpr int kTileOffSort = kTileHistWords;
+constexpr int kTileOffCap = kTileOffSort;              // the strip capture is read into registers before the columns are written
+constexpr int kTileOffList = kTileOffSort + kTileColRows * kBlkThreads;
+constexpr int kTileShOff = kTileOffList + kTileMaxInt + kTileListPad;
 constexpr int kTileBoxSmemWords = kTileShOff + (int)((sizeof(TileBoxShared) + 3) / 4);
 static_assert((kTileShOff * 4) % 16 == 0, "TileBoxShared alignment");
 
@@ -207,13 +204,51 @@ __device__ __forceinline__ TileBoxShared& tile_sh() {
   return *reinterpret_cast<TileBoxShared*>(smem_u32 + kTileShOff);
 }
 
-// pass over one sub-rect of the box: MODE 0 = pass 1 (reduce + histogram + capture of the in-bracket keys), MODE 1 = pass 2
-// (append the keys whose histogram word lies in [tgt, tgt + dt] to sortbuf)
-template <int MODE>
-__device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, int W, int rx0, int ry0, int rx1, int ry1,
-                                               uint32_t dmax_bits, const FrameTab& tb, float uc, float vc, float s4f, float kkf,
-                                               float ylo, float yhi, uint32_t hist_bias, AccQ& acc, float& s0_all, float& su,
-                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
+// one quad (4 pixels of one row) of a boundary strip: unproject + pose + min / max + sums as in lift_quad_kernel's pass 1, and in
+// KEY space: count the valid keys under lo, append the valid keys inside [lo, lo + dspan] to the capture buffer (one branch per
+// quad; rare on a boundary strip).  An invalid or masked pixel carries the key 0x7fffffff: over every bracket, under no lo.
+// cbelow = 1 - lo (mod 2^32): key in [1, lo - 1]  <=>  key - lo >= cbelow (unsigned; lo >= 2).
+__device__ __forceinline__ void accum_quad_strip(const uint4 q, const uint32_t (&dm)[4], float vr, float b0, float b1, float b2,
+                                                 const f32x2 (&cA)[3], const f32x2 (&cB)[3], AccQ& A, uint32_t lo, uint32_t cbelow,
+                                                 uint32_t dspan, int& n_below, uint32_t* capbuf, int* ncap) {
+  const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+  bool v[4];
+  uint32_t key[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = key_valid(bits[j], dm[j]);
+    key[j] = v[j] ? bits[j] : 0x7fffffffu;
+  }
+  const f32x2 dA = pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), dB = pack2(__uint_as_float(key[2]), __uint_as_float(key[3]));
+  const f32x2 vr2 = pack2(vr, vr);
+  float xa, xb;
+  f32x2 m;
+  m = mul2(dA, fma2(pack2(b0, b0), vr2, cA[0])); unpack2(m, xa, xb); A.mn0 = fmin3(A.mn0, xa, xb); A.mx0 = fmax3(A.mx0, xa, xb);
+  m = mul2(dB, fma2(pack2(b0, b0), vr2, cB[0])); unpack2(m, xa, xb); A.mn0 = fmin3(A.mn0, xa, xb); A.mx0 = fmax3(A.mx0, xa, xb);
+  m = mul2(dA, fma2(pack2(b1, b1), vr2, cA[1])); unpack2(m, xa, xb); A.mn1 = fmin3(A.mn1, xa, xb); A.mx1 = fmax3(A.mx1, xa, xb);
+  m = mul2(dB, fma2(pack2(b1, b1), vr2, cB[1])); unpack2(m, xa, xb); A.mn1 = fmin3(A.mn1, xa, xb); A.mx1 = fmax3(A.mx1, xa, xb);
+  m = mul2(dA, fma2(pack2(b2, b2), vr2, cA[2])); unpack2(m, xa, xb); A.mn2 = fmin3(A.mn2, xa, xb); A.mx2 = fmax3(A.mx2, xa, xb);
+  m = mul2(dB, fma2(pack2(b2, b2), vr2, cB[2])); unpack2(m, xa, xb); A.mn2 = fmin3(A.mn2, xa, xb); A.mx2 = fmax3(A.mx2, xa, xb);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (v[j]) { A.n_valid += 1.0f; A.s0[j] += __uint_as_float(bits[j]); A.sv = fmaf(vr, __uint_as_float(bits[j]), A.sv); }
+  const uint32_t u[4] = {key[0] - lo, key[1] - lo, key[2] - lo, key[3] - lo};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) n_below += (u[j] >= cbelow) ? 1 : 0;
+  if (min(min(u[0], u[1]), min(u[2], u[3])) <= dspan) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (u[j] <= dspan) {
+        const int pos = atomicAdd(ncap, 1);
+        if (pos < kTileStripCap) capbuf[pos] = key[j];
+      }
+  }
+}
+
+// the single pass over one boundary strip {rx0, ry0, rx1, ry1}
+__device__ __forceinline__ void tile_strip_pass(const float* __restrict__ fbase, int W, int rx0, int ry0, int rx1, int ry1, uint32_t dmax_bits,
+                                                const FrameTab& tb, float uc, float vc, AccQ& acc, float& s0_all, float& su, uint32_t lo,
+                                                uint32_t cbelow, uint32_t dspan, int& n_below, uint32_t* capbuf, int* ncap) {
   const int tid = threadIdx.x;
   const int rh = ry1 - ry0 + 1;
   const int xa = rx0 & ~3;
@@ -234,7 +269,7 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) dm[j] = (lane_ok && col0 + j >= rx0 && col0 + j <= rx1) ? dmax_bits : 0u;
     f32x2 cA[3], cB[3];
-    if (MODE == 0) {
+    {
       const float uf = (float)col0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -247,8 +282,7 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
     const float* gp = fbase + (uint32_t)((ry0 + row_l) * W + col0);
     float vr = (float)(ry0 + row_l) - vc;
     const int rows_l = rh - row_l;
-    uint32_t no_cptr = 0u;
-    if (MODE == 0) acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
+    acc.s0[0] = acc.s0[1] = acc.s0[2] = acc.s0[3] = 0.f;
     // a strip is short (a thread sees a handful of its row steps): the loads of kTileBatch steps are issued together
 #pragma unroll 1
     for (int st = 0; st < nsteps; st += kTileBatch) {
@@ -262,35 +296,13 @@ __device__ __forceinline__ void tile_rect_pass(const float* __restrict__ fbase, 
 #pragma unroll
       for (int i = 0; i < kTileBatch; ++i) {
         if (st + i >= nsteps) break;
-        const uint4 q0 = qb[i];
-        if (MODE == 0) {
-          accum_quad_hist<LM3D_TILE_STRIP_CAPTURE ? 2 : 0>(q0, dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, s4f, kkf, ylo, yhi, hist_bias, acc, tgt, dt,
-                                                           no_cptr, sortbuf, ncoll, kTileStripCap);
-          vr += frp;
-        } else {
-          const uint32_t bits[4] = {q0.x, q0.y, q0.z, q0.w};
-          float y[4];
-          unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
-          unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
-          const uint32_t u[4] = {__float_as_uint(y[0]) - tgt, __float_as_uint(y[1]) - tgt, __float_as_uint(y[2]) - tgt,
-                                 __float_as_uint(y[3]) - tgt};
-          if (min(min(u[0], u[1]), min(u[2], u[3])) <= dt) {  // one branch per quad
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (u[j] <= dt && key_valid(bits[j], dm[j])) {
-                const int pos = atomicAdd(ncoll, 1);
-                if (pos < kTileCollCap) sortbuf[pos] = bits[j];
-              }
-            }
-          }
-        }
+        accum_quad_strip(qb[i], dm, vr, tb.b[0], tb.b[1], tb.b[2], cA, cB, acc, lo, cbelow, dspan, n_below, capbuf, ncap);
+        vr += frp;
       }
     }
-    if (MODE == 0) {
-      const float du = (float)col0 - uc;
-      su = fmaf(du, acc.s0[0], fmaf(du + 1.f, acc.s0[1], fmaf(du + 2.f, acc.s0[2], fmaf(du + 3.f, acc.s0[3], su))));
-      s0_all += (acc.s0[0] + acc.s0[1]) + (acc.s0[2] + acc.s0[3]);
-    }
+    const float du = (float)col0 - uc;
+    su = fmaf(du, acc.s0[0], fmaf(du + 1.f, acc.s0[1], fmaf(du + 2.f, acc.s0[2], fmaf(du + 3.f, acc.s0[3], su))));
+    s0_all += (acc.s0[0] + acc.s0[1]) + (acc.s0[2] + acc.s0[3]);
   }
 }
 
@@ -311,19 +323,16 @@ __device__ __noinline__ void tile_prefetch_strips(const float* __restrict__ fbas
   }
 }
 
-// ---- phase: everything of pass 1 but the scan of the listed tiles.  Completely covered tiles contribute their TileSum
-//      (and go on the scan list when their depth range straddles the bracket [lo, hi]), the strips are walked pixel by
-//      pixel (reduce + histogram + capture); the per-warp partials go to shared memory. -----------------------------------
+// ---- phase: tile summaries + strips.  Completely covered tiles contribute their TileSum (and go on the scan list when their
+//      depth range straddles the coarse bracket [lo, hi]); the strips are walked pixel by pixel; the per-warp partials go to
+//      shared memory. ---------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void tile_pass1_sums(const float* __restrict__ fbase, int W, const TileSum* __restrict__ ts, int ntx_frame,
                                              const FrameTab* __restrict__ tab_f, uint32_t dmax_bits, uint32_t lo, uint32_t hi,
-                                             float uc, float vc, float s4f, float kkf) {
+                                             float uc, float vc) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   TileBoxShared& sh = tile_sh();
-  uint32_t* sortbuf = smem_u32 + kTileHistWords;
-  uint32_t* scan_list = sortbuf + kSortCap;
+  uint32_t* scan_list = smem_u32 + kTileOffList;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t hist_bias = (uint32_t)__cvta_generic_to_shared(smem_u32) - 0x30000000u;
-  const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
   AccQ acc;
   acc.mn0 = acc.mn1 = acc.mn2 = INFINITY;
   acc.mx0 = acc.mx1 = acc.mx2 = -INFINITY;
@@ -348,171 +357,255 @@ __device__ __noinline__ void tile_pass1_sums(const float* __restrict__ fbase, in
         dsv += (double)a.w + ((double)(ty * kTile) + 7.5 - (double)vc) * s0;
         acc.mn0 = fminf(acc.mn0, m.x); acc.mn1 = fminf(acc.mn1, m.y); acc.mn2 = fminf(acc.mn2, m.z);
         acc.mx0 = fmaxf(acc.mx0, m.w); acc.mx1 = fmaxf(acc.mx1, x.x); acc.mx2 = fmaxf(acc.mx2, x.y);
-        // depth range vs the bracket [lo, hi] (keys): all under -> counted, all over -> nothing, else scanned
+        // depth range vs the bracket [lo, hi] (keys): all under -> counted, all over -> nothing, else listed
         if (__float_as_uint(x.w) < lo) below_t += nv;
         else if (__float_as_uint(x.z) <= hi) {
           scan_list[atomicAdd(&sh.n_scan, 1)] = (uint32_t)((ty * kTile) * W + tx * kTile);
           nvs_t += nv;
-          over_t |= (rawmax > dmax_f) ? 1 : 0;  // the tile holds a pixel over max_depth (or +inf): the light pass must test validity
+          over_t |= (rawmax > dmax_f) ? 1 : 0;  // the tile holds a pixel over max_depth (or +inf): pass A must test validity
         }
       }
     }
   }
   float s0_all = 0.f, su = 0.f;
+  int sb_t = 0;  // strip keys under lo
   {
     const FrameTab tb = load_tab(tab_f, 0);
     const int n_sr = sh.n_sr;
 #pragma unroll 1
     for (int s = 0; s < n_sr; ++s)
-      tile_rect_pass<0>(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], dmax_bits, tb, uc, vc, s4f, kkf, ylo, yhi, hist_bias,
-                        acc, s0_all, su, 0x4C000000u + 256u, (uint32_t)kBlkBins - 1u, sortbuf + kTileCollCap, &sh.ncap);
+      tile_strip_pass(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], dmax_bits, tb, uc, vc, acc, s0_all, su, lo, 1u - lo, hi - lo,
+                      sb_t, smem_u32 + kTileOffCap, &sh.ncap);
   }
   const int nv_strips_l = (int)acc.n_valid;
   const double d0 = warp_sum_d(ds0 + (double)s0_all), d1 = warp_sum_d(dsu + (double)su), d2 = warp_sum_d(dsv + (double)acc.sv);
   const float f0 = warp_min_f(acc.mn0), f1 = warp_min_f(acc.mn1), f2 = warp_min_f(acc.mn2);
   const float f3 = warp_max_f(acc.mx0), f4 = warp_max_f(acc.mx1), f5 = warp_max_f(acc.mx2);
   const int i0 = warp_sum_i(nv_t + nv_strips_l), i1 = warp_sum_i(nv_strips_l), i2 = warp_sum_i(below_t), i3 = warp_sum_i(nvs_t);
-  const int i4 = __any_sync(kFull, over_t != 0) ? 1 : 0;
+  const int i4 = __any_sync(kFull, over_t != 0) ? 1 : 0, i5 = warp_sum_i(sb_t);
   if (lane == 0) {
     sh.red_d[warp][0] = d0; sh.red_d[warp][1] = d1; sh.red_d[warp][2] = d2;
     sh.red_f[warp][0] = f0; sh.red_f[warp][1] = f1; sh.red_f[warp][2] = f2;
     sh.red_f[warp][3] = f3; sh.red_f[warp][4] = f4; sh.red_f[warp][5] = f5;
     sh.red_i[warp][0] = i0; sh.red_i[warp][1] = i1; sh.red_i[warp][2] = i2; sh.red_i[warp][3] = i3; sh.red_i[warp][4] = i4;
+    sh.red_i[warp][5] = i5;
   }
 }
 
-// ---- phase: light pass over the listed tiles (completely inside the rect and the frame: no masks, no geometry).  The 64
-//      quads of a tile go to 64 consecutive threads, so a thread keeps ONE (row, quad column) position and walks the tiles
-//      four apart.  Fed by a cp.async ring: the thread's quad of tile m + kTileRing is requested (LDGSTS, no registers held)
-//      before its quad of tile m is reduced (register-held batches cap the loads in flight at the register budget:
-//      2.82 ms vs 2.27 ms on C3 x 200 frames).
-//      MODE 0: histogram update.  CHECK = false when no listed tile holds an over-range pixel and the map sends every
-//      d <= 0 under the bins: then an invalid pixel (0, negative, NaN) lands in the private "below" words through the clamp
-//      alone, exactly where the validity select would have sent it, and the 12 instructions per quad of the test go.
-//      MODE 1: collect the keys whose histogram word lies in [tgt, tgt + dt] (a packed fma and one branch per quad). -----
-constexpr int kTileRing = LM3D_TILE_RING;
-// what a scan pass does with one quad of a listed tile
-template <int MODE, bool CHECK>
-__device__ __forceinline__ void tile_scan_quad(const uint4 q, uint32_t dmax_bits, float s4f, float kkf, float ylo, float yhi, uint32_t hist_bias,
-                                               uint32_t tgt, uint32_t dt, uint32_t* sortbuf, int* ncoll) {
-  const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
-  float y[4];
-  if (MODE == 0) {
+// ---- phase: pass A.  One pixel row in kTileStride (rows p, p + 4, p + 8, p + 12 with p = list index & 3) of EVERY listed tile goes
+//      through the bracket histogram: the map of lift_block_kernel, 1000 bins across the coarse bracket between thread-private
+//      "below" / "above" words.  A 64-thread group takes four consecutive list entries per step, 16 threads = 16 quads per tile.
+//      CHECK = false when no listed tile holds an over-range pixel and the map sends every d <= 0 under the bins: an invalid
+//      pixel (0, negative, NaN) then lands in the private "below" words through the clamp alone, exactly where the validity
+//      select would have sent it, and the 12 instructions per quad of the test go.  The counts are an ESTIMATE (x 4) that
+//      steers pass B; nothing of the result depends on them. ------------------------------------------------------------------
+template <bool CHECK>
+__device__ __noinline__ void tile_sample_pass(const float* __restrict__ fbase, int W, int n_scan, uint32_t dmax_bits, float s4f, float kkf) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int tid = threadIdx.x, t = tid & 63;
+  const uint32_t* scan_list = smem_u32 + kTileOffList;
+  const uint32_t hist_bias = (uint32_t)__cvta_generic_to_shared(smem_u32) - 0x30000000u;
+  const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
+  const int sub = t >> 4;                                         // which of the group's four tiles; also the row phase (list index & 3)
+  const float* __restrict__ qp = fbase + ((4 * ((t & 15) >> 2) + sub) * W + (t & 3) * 4);
+  const int idx0 = 4 * (tid >> 6) + sub;                          // list index of step 0; + 16 per step
+  const int n_it = (n_scan + 15) >> 4;
+  auto load = [&](int it) { return ldg_u4(qp + scan_list[min(idx0 + 16 * it, n_scan)]); };  // (entry n_scan is a zero pad)
+  auto reduce = [&](const uint4 q, int it) {
+    if (idx0 + 16 * it >= n_scan) return;
+    const uint32_t bits[4] = {q.x, q.y, q.z, q.w};
     uint32_t key[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) key[j] = (!CHECK || key_valid(bits[j], dmax_bits)) ? bits[j] : 0x7fffffffu;
+    float y[4];
     unpack2(fma2(pack2(__uint_as_float(key[0]), __uint_as_float(key[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
     unpack2(fma2(pack2(__uint_as_float(key[2]), __uint_as_float(key[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float yc = fminf(fmaxf(y[j], ylo), yhi);  // NaN -> ylo
+      asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias), "r"(kTileStride) : "memory");  // a sampled pixel stands for kTileStride
+    }
+  };
+  {
+    // the strips' keys inside the coarse bracket are a census, not a sample: weight 1 (they all map into the bins or their margins)
+    const uint32_t* capbuf = smem_u32 + kTileOffCap;
+    const int ncap = min(tile_sh().ncap, kTileStripCap);
+    for (int i = tid; i < ncap; i += kBlkThreads) {
+      const float yc = fminf(fmaxf(fmaf(__uint_as_float(capbuf[i]), s4f, kkf), ylo), yhi);
       asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__float_as_uint(yc) * 4u + hist_bias) : "memory");
     }
-  } else {
-    unpack2(fma2(pack2(__uint_as_float(bits[0]), __uint_as_float(bits[1])), pack2(s4f, s4f), pack2(kkf, kkf)), y[0], y[1]);
-    unpack2(fma2(pack2(__uint_as_float(bits[2]), __uint_as_float(bits[3])), pack2(s4f, s4f), pack2(kkf, kkf)), y[2], y[3]);
-    // one branch per quad: the smallest distance to the target words decides whether any pixel can match
-    const uint32_t u[4] = {__float_as_uint(y[0]) - tgt, __float_as_uint(y[1]) - tgt, __float_as_uint(y[2]) - tgt,
-                           __float_as_uint(y[3]) - tgt};
-    if (min(min(u[0], u[1]), min(u[2], u[3])) <= dt) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (u[j] <= dt && key_valid(bits[j], dmax_bits)) {
-          const int pos = atomicAdd(ncoll, 1);
-          if (pos < kTileCollCap) sortbuf[pos] = bits[j];
-        }
-      }
-    }
   }
-}
-
-template <int MODE, bool CHECK>
-__device__ __noinline__ void tile_scan_pass(const float* __restrict__ fbase, int W, int n_scan, uint32_t dmax_bits, float s4f, float kkf,
-                                            uint32_t tgt, uint32_t dt) {
-  extern __shared__ __align__(16) uint32_t smem_u32[];
-  const int tid = threadIdx.x;
-  uint32_t* sortbuf = smem_u32 + kTileHistWords;
-  const uint32_t* scan_list = sortbuf + kSortCap + (tid >> 6);      // the 64-thread group takes tiles g, g + 4, g + 8, ...
-  int* ncoll = &tile_sh().ncoll;
-  const uint32_t hist_bias = (uint32_t)__cvta_generic_to_shared(smem_u32) - 0x30000000u;
-  const float ylo = 33554432.f + 4.f * (float)tid, yhi = 33554432.f + 4.f * (float)(256 + kBlkBins + tid);
-  const float* __restrict__ qp = fbase + (((tid & 63) >> 2) * W + (tid & 3) * 4);  // (row, quad column) inside a tile
-  const int n_my = (n_scan - (tid >> 6) + 3) >> 2;     // (same for the 64 threads of a group: warp-uniform control)
-  // (the list is padded with kTileListPad zero offsets: requests past the end read the frame's first tile and are dropped)
-#if LM3D_TILE_SCAN_LDG
   uint4 qa[4], qb[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * i]);
+  for (int i = 0; i < 4; ++i) qa[i] = load(i);
 #pragma unroll 1
-  for (int m0 = 0; m0 < n_my; m0 += 8) {
+  for (int m0 = 0; m0 < n_it; m0 += 8) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qb[i] = ldg_u4(qp + scan_list[4 * (m0 + 4 + i)]);
+    for (int i = 0; i < 4; ++i) qb[i] = load(m0 + 4 + i);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (m0 + i < n_my) tile_scan_quad<MODE, CHECK>(qa[i], dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
-    if (m0 + 4 >= n_my) break;
+    for (int i = 0; i < 4; ++i) reduce(qa[i], m0 + i);
+    if (m0 + 4 >= n_it) break;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * (m0 + 8 + i)]);
+    for (int i = 0; i < 4; ++i) qa[i] = load(m0 + 8 + i);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (m0 + 4 + i < n_my) tile_scan_quad<MODE, CHECK>(qb[i], dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
+    for (int i = 0; i < 4; ++i) reduce(qb[i], m0 + 4 + i);
   }
-#else
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem_u32 + kTileHistWords + kSortCap + kTileMaxInt + kTileListPad) + (uint32_t)tid * 16;
-  constexpr uint32_t kSlot = kBlkThreads * 16;
-#pragma unroll
-  for (int i = 0; i < kTileRing; ++i) {
-    cp_async_16(ring_s + i * kSlot, qp + scan_list[4 * i], 16u);
-    cp_async_commit();
-  }
-#pragma unroll 1
-  for (int m0 = 0; m0 < n_my; m0 += kTileRing) {
-#pragma unroll
-    for (int i = 0; i < kTileRing; ++i) {
-      const int m = m0 + i;
-      if (m >= n_my) break;
-      cp_async_wait<kTileRing - 1>();
-      const uint4 q = lds_u4(ring_s + i * kSlot);
-      cp_async_16(ring_s + i * kSlot, qp + scan_list[4 * (m + kTileRing)], 16u);
-      cp_async_commit();
-      tile_scan_quad<MODE, CHECK>(q, dmax_bits, s4f, kkf, ylo, yhi, hist_bias, tgt, dt, sortbuf, ncoll);
-    }
-  }
-  cp_async_wait<0>();  // drain the requests past the end before the slots are reused
-#endif
 }
 
-// ---- phase: pass 2 over the strips.  Their keys that fell into a bracket bin were captured by pass 1; when the capture
-//      buffer overflowed (a box whose strips hold thousands of in-bracket keys) the strips are walked again. -----------------
-__device__ __noinline__ void tile_strips_pass2(const float* __restrict__ fbase, int W, uint32_t dmax_bits, float s4f, float kkf, uint32_t tgt,
-                                               uint32_t dt) {
+// ---- phase: pass B + select.  Every pixel of the listed tiles (the 64 quads of a tile go to 64 consecutive threads; a thread keeps
+//      ONE (row, quad column) position and walks the tiles four apart; two register batches of four LDG.128, ping-pong), in key
+//      space: u = bits - lo'; a valid key under lo' <=> u >= 1 - lo' (one compare, one predicated add); a key of the narrow
+//      bracket <=> u <= hi' - lo' -> appended to the thread's PRIVATE column (a predicated store + pointer bump: no atomics, no
+//      ballot, no branch; 1500 hits over 256 threads are ~6 per column of 36).  Whatever is not a valid depth -- 0, negatives,
+//      NaN, inf, values over max_depth >= hi' -- fails both tests, so there is no validity test and no shared-memory traffic but
+//      the hits.  The captured strip keys go through the same tests first.  Then the order statistics rl = rbase - (keys under
+//      lo') and rl + 1 of the collected keys: up to 256 keys are gathered (block scan of the column heights) and a thread per
+//      key counts the keys under / equal to its own (broadcast reads, one barrier instead of the ~30 of a bitonic sort); more
+//      keys take one key-space histogram round (1024 bins across the narrow bracket) in front of that.
+//      Returns 0 with the two keys in sh.sel, or a reason for handing the box to lift_block_kernel: 1 = a column ran over,
+//      2 = the narrow bracket missed the rank, 3 = ties put more than 256 keys into the target bins. ----------------------------
+constexpr int kTileColGuard = 4;                                        // a quad may append 4 keys before the pointer is clamped
+__device__ __forceinline__ void tile_count_key(uint32_t bits, uint32_t lo2, uint32_t cbelow2, uint32_t dspan2, int& n_below, uint32_t& ptr) {
+  const uint32_t u = bits - lo2;
+  n_below += (u >= cbelow2) ? 1 : 0;
+  asm volatile("{\n.reg .pred p;\nsetp.le.u32 p, %2, %3;\n@p st.shared.u32 [%0], %1;\n@p add.u32 %0, %0, %4;\n}"
+               : "+r"(ptr) : "r"(bits), "r"(u), "r"(dspan2), "n"(kBlkThreads * 4) : "memory");
+}
+__device__ __noinline__ int tile_count_select(const float* __restrict__ fbase, int W, int n_scan, uint32_t lo2, uint32_t dspan2, int rbase, int two) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   TileBoxShared& sh = tile_sh();
-  uint32_t* sortbuf = smem_u32 + kTileHistWords;
-#if LM3D_TILE_STRIP_CAPTURE
-  const int ncap = sh.ncap;
-  if (ncap <= kTileStripCap) {
-    const uint32_t* capbuf = sortbuf + kTileCollCap;
-    for (int i = threadIdx.x; i < ncap; i += kBlkThreads) {
-      const uint32_t key = capbuf[i];
-      if (__float_as_uint(fmaf(__uint_as_float(key), s4f, kkf)) - tgt <= dt) {
-        const int pos = atomicAdd(&sh.ncoll, 1);
-        if (pos < kTileCollCap) sortbuf[pos] = key;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* hist = smem_u32;
+  const uint32_t* col = smem_u32 + kTileOffSort + tid;
+  const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(smem_u32 + kTileOffSort + tid);
+  const uint32_t end_s = col_s + (uint32_t)(kTileColRows - kTileColGuard) * (kBlkThreads * 4);
+  const uint32_t cbelow2 = 1u - lo2;
+  uint32_t ptr = col_s;
+  int n_below = 0;
+  {
+    // the strips' keys inside the coarse bracket: out of the capture buffer first (the columns overlay it)
+    const uint32_t* capbuf = smem_u32 + kTileOffCap;
+    const int ncap = sh.ncap;
+    uint32_t sk[kTileStripCap / kBlkThreads];
+#pragma unroll
+    for (int e = 0; e < kTileStripCap / kBlkThreads; ++e) sk[e] = (e * kBlkThreads + tid < ncap) ? capbuf[e * kBlkThreads + tid] : 0x7fffffffu;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kTileStripCap / kBlkThreads; ++e) tile_count_key(sk[e], lo2, cbelow2, dspan2, n_below, ptr);
+    ptr = min(ptr, end_s);
+  }
+  {
+    const uint32_t* scan_list = smem_u32 + kTileOffList + (tid >> 6);  // the 64-thread group takes tiles g, g + 4, g + 8, ...
+    const float* __restrict__ qp = fbase + (((tid & 63) >> 2) * W + (tid & 3) * 4);  // (row, quad column) inside a tile
+    const int n_my = (n_scan - (tid >> 6) + 3) >> 2;     // (same for the 64 threads of a group: warp-uniform control)
+    auto quad = [&](const uint4 q) {
+      tile_count_key(q.x, lo2, cbelow2, dspan2, n_below, ptr);
+      tile_count_key(q.y, lo2, cbelow2, dspan2, n_below, ptr);
+      tile_count_key(q.z, lo2, cbelow2, dspan2, n_below, ptr);
+      tile_count_key(q.w, lo2, cbelow2, dspan2, n_below, ptr);
+      ptr = min(ptr, end_s);
+    };
+    // (the list is padded with kTileListPad zero offsets: requests past the end read the frame's first tile and are dropped)
+    uint4 qa[4], qb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * i]);
+#pragma unroll 1
+    for (int m0 = 0; m0 < n_my; m0 += 8) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qb[i] = ldg_u4(qp + scan_list[4 * (m0 + 4 + i)]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (m0 + i < n_my) quad(qa[i]);
+      if (m0 + 4 >= n_my) break;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * (m0 + 8 + i)]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (m0 + 4 + i < n_my) quad(qb[i]);
+    }
+  }
+  // ---- block totals: keys under lo', collected keys (with each thread's offset), overflow ----------------------------------
+  const int cnt = (int)((ptr - col_s) / (kBlkThreads * 4));
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  n_below = warp_sum_i(n_below);
+  const bool over = __any_sync(kFull, ptr >= end_s);
+  if (lane == 31) { sh.scan_w[warp] = incl; sh.red_b[warp] = over ? -1 : n_below; }
+  if (tid == 0) { sh.b_lo = -1; sh.b_hi = -1; sh.before = 0; sh.nsmall = 0; }
+  __syncthreads();
+  int off = incl - cnt, n_coll = 0, below2 = 0;
+  bool overflow = false;
+#pragma unroll
+  for (int w = 0; w < kBlkWarps; ++w) {
+    if (w < warp) off += sh.scan_w[w];
+    n_coll += sh.scan_w[w];
+    overflow |= sh.red_b[w] < 0;
+    below2 += sh.red_b[w];
+  }
+  if (tid == 0) sh.ncoll = n_coll;
+  if (overflow) return 1;
+  int rl = rbase - below2;
+  if (rl < 0 || rl + two >= n_coll) return 2;
+  uint32_t* small = hist + 1024;  // [256] keys for the rank select
+  int n = n_coll;
+  if (n_coll <= kBlkThreads) {
+    for (int k = 0; k < cnt; ++k) small[off + k] = col[k * kBlkThreads];
+  } else {
+    const int shift = max(0, 22 - __clz(dspan2 | 1u));  // (dspan2 >> shift) <= 1023
+    for (int i = tid; i < 1024; i += kBlkThreads) hist[i] = 0u;
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) atomicAdd(&hist[(col[k * kBlkThreads] - lo2) >> shift], 1u);
+    __syncthreads();
+    const uint4 h4 = reinterpret_cast<const uint4*>(hist)[tid];
+    const int c4[4] = {(int)h4.x, (int)h4.y, (int)h4.z, (int)h4.w};
+    const int c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+    int inc2 = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, inc2, o);
+      if (lane >= o) inc2 += v;
+    }
+    __syncthreads();  // (scan_w is read above)
+    if (lane == 31) sh.scan_w[warp] = inc2;
+    __syncthreads();
+    int cum = inc2 - c;
+#pragma unroll
+    for (int w = 0; w < kBlkWarps; ++w) if (w < warp) cum += sh.scan_w[w];
+    const int r1 = rl + two;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (rl >= cum && rl < cum + c4[i]) { sh.b_lo = 4 * tid + i; sh.before = cum; }
+      if (r1 >= cum && r1 < cum + c4[i]) sh.b_hi = 4 * tid + i;
+      cum += c4[i];
+    }
+    __syncthreads();
+    const uint32_t b_lo = (uint32_t)sh.b_lo, db = (uint32_t)(sh.b_hi - sh.b_lo);
+    for (int k = 0; k < cnt; ++k) {
+      const uint32_t key = col[k * kBlkThreads];
+      if (((key - lo2) >> shift) - b_lo <= db) {
+        const int pos = atomicAdd(&sh.nsmall, 1);
+        if (pos < kBlkThreads) small[pos] = key;
       }
     }
-    return;
+    __syncthreads();
+    n = sh.nsmall;
+    if (sh.b_lo < 0 || sh.b_hi < sh.b_lo || n > kBlkThreads) return 3;
+    rl -= sh.before;
   }
-#endif
-  FrameTab tb;  // (not read by MODE 1)
-#pragma unroll
-  for (int k = 0; k < 3; ++k) tb.a[k] = tb.b[k] = tb.c[k] = tb.t[k] = 0.f;
-  AccQ acc;
-  float d0 = 0.f, d1 = 0.f;
-  const int n_sr = sh.n_sr;
-#pragma unroll 1
-  for (int s = 0; s < n_sr; ++s)
-    tile_rect_pass<1>(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], dmax_bits, tb, 0.f, 0.f, s4f, kkf, 0.f, 0.f, 0u, acc, d0, d1,
-                      tgt, dt, sortbuf, &sh.ncoll);
+  __syncthreads();
+  if (tid < n) {
+    const uint32_t key = small[tid];
+    int less = 0, eq = 0;
+    for (int i = 0; i < n; ++i) { const uint32_t o = small[i]; less += (o < key); eq += (o == key); }
+    if (less <= rl && rl < less + eq) sh.sel[0] = key;
+    if (less <= rl + 1 && rl + 1 < less + eq) sh.sel[1] = key;
+  }
+  __syncthreads();
+  return 0;
 }
 
 // LM3D_TILE_TIMING (dev builds only): thread 0 of every CTA adds the clock64() cycles of each phase of a box to
@@ -524,12 +617,11 @@ __device__ unsigned long long g_tile_prof[16];
 #define TILE_T(ph) do { } while (0)
 #endif
 #ifndef LM3D_TILE_MINB
-#define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers beats 2 CTAs at 124 and 4 at 64 (C3 x 200: 2.27 / 2.41 / 2.41 ms)
+#define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers; 4 x 64 registers measured equal (the kernel is bound by the SM's throughput, not by latency)
 #endif
 __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(const TileArgs T) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* hist = smem_u32;                           // [256 | kBlkBins | 256] as in lift_block_kernel
-  uint32_t* sortbuf = smem_u32 + kTileHistWords;       // [kSortCap]: [0, 2048) the collected keys, [2048, 4096) the strips' capture
   TileBoxShared& sh = tile_sh();
   const LiftArgs& A = T.A;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -566,7 +658,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       int n_sr = 0;
       auto strip = [&](int x0, int y0, int x1, int y1) { sh.sr[n_sr][0] = x0; sh.sr[n_sr][1] = y0; sh.sr[n_sr][2] = x1; sh.sr[n_sr][3] = y1; ++n_sr; };
       if (!has_int) {
-        strip(rc.x0, rc.y0, rc.x1, rc.y1);
+        n_sr = -1;  // no completely covered tile (or more than the list holds): nothing to gain here, lift_block_kernel takes the box
       } else {
         const int iy0 = ty_lo * kTile, iy1 = (ty_hi + 1) * kTile - 1;
         const int ix0 = tx_lo * kTile, ix1 = (tx_hi + 1) * kTile - 1;
@@ -579,17 +671,27 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       sh.n_scan = 0; sh.ncoll = 0; sh.ncap = 0;
     }
     __syncthreads();
+    if (sh.n_sr < 0 || A.dmax_bits < 2u) {  // (uniform)
+      if (tid == 0) {
+        const int pos = atomicAdd(&A.counters[1], 1);
+        const_cast<int32_t*>(A.list)[pos] = b;
+        atomicAdd(&A.counters[14], 1);
+      }
+      continue;
+    }
 #if LM3D_TILE_PREFETCH
     tile_prefetch_strips(fbase, W);
 #endif
     TILE_T(0);
 
-    // ---- lattice sample -> bracket [lo, hi] in key space (binned, no sort: block_bracket_binned) --------------------
+    // ---- lattice sample -> coarse bracket [lo, hi] in key space (binned, no sort: block_bracket_binned) -------------
     uint32_t lo = 1u, hi = kKeyMaxValid;
     block_bracket_binned<kTileSample>(fbase, W, rc, A.dmax_bits, A.quant, kTileBracketZ, hist, sh.ls, lo, hi);
     hi = min(hi, A.dmax_bits);
+    lo = min(max(lo, 2u), max(hi, 2u));  // (lo >= 2: the wrap-around compare of the key-space tests needs 1 - lo != 0)
+    hi = max(hi, lo);
     TILE_T(1);
-    const float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(max(hi, 1u));
+    const float wlo_f = __uint_as_float(lo), whi_f = __uint_as_float(hi);
     const float wd = whi_f - wlo_f;
     const float s4f = (wd > 0.f) ? fminf(4000.f / wd, 2097152.f / whi_f) : 0.f;  // 1000 bins x 4
     const float kkf = fmaf(-wlo_f, s4f, 33554432.f + 4.f * 268.f);               // window low edge -> word 268
@@ -597,29 +699,19 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
     for (int i = tid; i < kTileHistWords; i += kBlkThreads) hist[i] = 0u;
     __syncthreads();
 
-    // ---- pass 1: tile summaries + strips, then the light pass over the listed tiles -----------------------------
-    tile_pass1_sums(fbase, W, T.tsum + (size_t)slot * n_tiles, T.ntx, A.tab + f, A.dmax_bits, lo, hi, uc, vc, s4f, kkf);
+    // ---- tile summaries + strips -------------------------------------------------------------------------------
+    tile_pass1_sums(fbase, W, T.tsum + (size_t)slot * n_tiles, T.ntx, A.tab + f, A.dmax_bits, lo, hi, uc, vc);
     __syncthreads();
     TILE_T(3);
     const int n_scan = sh.n_scan;
-    if (tid < kTileListPad) sortbuf[kSortCap + n_scan + tid] = 0u;  // pad the scan list for the ring's requests past its end
+    if (tid < kTileListPad) smem_u32[kTileOffList + n_scan + tid] = 0u;  // pad the scan list for the batched loads past its end
     __syncthreads();
-    {
-      int over = 0;
-#pragma unroll
-      for (int w = 0; w < kBlkWarps; ++w) over |= sh.red_i[w][4];
-      // the clamp alone sorts invalid pixels iff every d <= 0 maps under the bins (kkf = the image of 0) and nothing listed is over range
-      if (over || !(kkf < 33554432.f + 4.f * 256.f)) tile_scan_pass<0, true>(fbase, W, n_scan, A.dmax_bits, s4f, kkf, 0u, 0u);
-      else tile_scan_pass<0, false>(fbase, W, n_scan, A.dmax_bits, s4f, kkf, 0u, 0u);
-    }
-    __syncthreads();
-    TILE_T(4);
 
     // ---- block reduction of the per-warp partials ---------------------------------------------------------------
     BoxSums S;
     S.s0 = S.su = S.sv = 0.0;
     S.n_valid = 0;
-    int nv_strips = 0, below_tiles = 0, nv_scanned = 0;
+    int nv_strips = 0, below_tiles = 0, nv_scanned = 0, over = 0, strips_below = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { S.mn[k] = INFINITY; S.mx[k] = -INFINITY; }
     for (int w = 0; w < kBlkWarps; ++w) {
@@ -633,93 +725,85 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       nv_strips += sh.red_i[w][1];
       below_tiles += sh.red_i[w][2];
       nv_scanned += sh.red_i[w][3];
+      over |= sh.red_i[w][4];
+      strips_below += sh.red_i[w][5];
     }
-
-    // ---- which bins hold the target ranks?  thread t owns bin words 256 + 4 t .. + 3 ------------------------------
     int r = 0; bool two = false; double gamma = 0.0;
     if (S.n_valid > 0) order_ranks(S.n_valid, A.quant, r, two, gamma);
-    const int r1 = r + (two ? 1 : 0);
     uint32_t k0 = 0, k1 = 0;
     bool handover = false;
     if (S.n_valid > 0) {
-      const int below_all = block_sum_i((int)hist[tid], sh.ls, 0), above = block_sum_i((int)hist[256 + kBlkBins + tid], sh.ls, 1);
-      const uint4 h4 = reinterpret_cast<const uint4*>(hist + 256)[tid];
-      const int c4[4] = {(int)h4.x, (int)h4.y, (int)h4.z, (int)h4.w};
-      const int c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-      }
+      const int ncap = sh.ncap;
+      // ---- pass A: a quarter of the listed tiles' pixels through the bracket histogram -> narrow bracket [lo2, hi2] ------
+      // (the clamp alone sorts invalid pixels iff every d <= 0 maps under the bins -- kkf is the image of 0 -- and nothing listed is over range)
+      if (over || !(kkf < 33554432.f + 4.f * 256.f)) tile_sample_pass<true>(fbase, W, n_scan, A.dmax_bits, s4f, kkf);
+      else tile_sample_pass<false>(fbase, W, n_scan, A.dmax_bits, s4f, kkf);
       __syncthreads();
-      if (lane == 31) sh.scan_w[warp] = incl;
-      if (tid == 0) { sh.b_lo = -1; sh.b_hi = -1; sh.before = 0; sh.end = 0; }
-      __syncthreads();
-      int wpre = 0, in_all = 0;
+      TILE_T(4);
+      uint32_t lo2 = lo, hi2 = hi;
+      {
+        const int below_all = block_sum_i((int)hist[tid], sh.ls, 0);
+        const uint4 h4 = reinterpret_cast<const uint4*>(hist + 256)[tid];
+        const int c4[4] = {(int)h4.x, (int)h4.y, (int)h4.z, (int)h4.w};
+        const int c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+        int incl = c;
 #pragma unroll
-      for (int w = 0; w < kBlkWarps; ++w) { if (w < warp) wpre += sh.scan_w[w]; in_all += sh.scan_w[w]; }
-      // Every histogram update is one slot; the slots that were not valid pixels (masked strip lanes, invalid pixels
-      // of strips and scanned tiles) all sit in the private "below" words.  Valid keys that went through the
-      // histogram = strips + scanned tiles (their counts are known), so the valid keys under the bracket are
-      // below_all - (slots - valid), plus the tiles that were counted as "all under" without a scan.
-      const int slots = below_all + in_all + above;
-      const int below = below_tiles + below_all - (slots - nv_strips - nv_scanned);
-      int cum = below + wpre + incl - c;  // valid keys before this thread's bins
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (r >= cum && r < cum + c4[i]) { sh.b_lo = 256 + 4 * tid + i; sh.before = cum; }
-        if (r1 >= cum && r1 < cum + c4[i]) { sh.b_hi = 256 + 4 * tid + i; sh.end = cum + c4[i]; }
-        cum += c4[i];
-      }
-      __syncthreads();
-      const int b_lo = sh.b_lo, b_hi = sh.b_hi, before = sh.before;
-      const int n_coll = sh.end - before;
-      if (b_lo < 256 || b_hi < b_lo || n_coll > kTileCollCap) {
-        // the bracket missed the rank (3 sigma of the sample: a few boxes per thousand), or ties overfill the target
-        // bins: lift_block_kernel refines.  (A retry loop around this body was measured: the live ranges it adds
-        // cost 35 % of the kernel -- 128 registers and spills -- to save the 0.5 ms tail of a few handed-over boxes.)
-        handover = true;
-      } else {
-        const uint32_t tgt = 0x4C000000u + (uint32_t)b_lo, dt = (uint32_t)(b_hi - b_lo);
-        TILE_T(5);
-        tile_strips_pass2(fbase, W, A.dmax_bits, s4f, kkf, tgt, dt);
-#ifdef LM3D_TILE_TIMING
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += t;
+        }
         __syncthreads();
-#endif
-        TILE_T(6);
-        tile_scan_pass<1, true>(fbase, W, n_scan, A.dmax_bits, s4f, kkf, tgt, dt);
+        if (lane == 31) sh.scan_w[warp] = incl;
+        if (tid == 0) { sh.b_lo = -1; sh.b_hi = -1; }
         __syncthreads();
-        TILE_T(7);
-        if (sh.ncoll != n_coll) {
-          handover = true;  // (cannot happen: both passes evaluate the same map)
-          if (tid == 0) atomicAdd(&A.counters[15], 1);
-        } else {
-          const int rl = r - before;
-          if (n_coll <= kBlkThreads) {
-            // a thread per key: its rank = keys under it, its multiplicity = keys equal to it (broadcast reads, one barrier
-            // instead of the ~30 of a bitonic sort of 64-256 keys)
-            if (tid < n_coll) {
-              const uint32_t key = sortbuf[tid];
-              int less = 0, eq = 0;
-              for (int i = 0; i < n_coll; ++i) { const uint32_t o = sortbuf[i]; less += (o < key); eq += (o == key); }
-              if (less <= rl && rl < less + eq) sh.sel[0] = key;
-              if (less <= rl + 1 && rl + 1 < less + eq) sh.sel[1] = key;
-            }
-            __syncthreads();
-            k0 = sh.sel[0];
-            k1 = two ? sh.sel[1] : k0;
-          } else {
-            int np2 = 512;
-            while (np2 < n_coll) np2 <<= 1;
-            for (int i = n_coll + tid; i < np2; i += kBlkThreads) sortbuf[i] = kKeyInvalid;
-            block_bitonic(sortbuf, np2);
-            k0 = sortbuf[rl];
-            k1 = two ? sortbuf[rl + 1] : k0;
-            __syncthreads();
+        int wpre = 0;
+#pragma unroll
+        for (int w = 0; w < kBlkWarps; ++w) if (w < warp) wpre += sh.scan_w[w];
+        // The histogram is in KEYS: a sampled pixel of a listed tile counted kTileStride, a captured strip key 1.  The private "below"
+        // words also hold the sampled slots that were not valid pixels (x kTileStride); their number is estimated from the tiles'
+        // valid counts.  What the estimate may be off by is the sampling error: worst case sigma^2 = N (stride - 1) / 4 for N listed keys.
+        const int inv_s = n_scan * 256 - nv_scanned;
+        const int bs = max(0, below_all - inv_s);                          // valid keys of the listed tiles (and captured strip keys) under the bins
+        const int rs = r - below_tiles - strips_below;                     // rank among the listed tiles' + captured strip keys
+        const int m = (int)(kTileNarrowZ * 0.5f * sqrtf((float)(kTileStride - 1) * (float)nv_scanned)) + 2 * kTileStride;
+        const int xa = rs - m, xb = rs + (two ? 1 : 0) + 1 + m;
+        int cum = bs + wpre + incl - c;  // keys before this thread's bins
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (xa >= cum && xa < cum + c4[i]) sh.b_lo = 256 + 4 * tid + i;
+          if (xb >= cum && xb < cum + c4[i]) sh.b_hi = 256 + 4 * tid + i;
+          cum += c4[i];
+        }
+        __syncthreads();
+        // bin edges -> keys: word w starts at depth wlo + 4 (w - 268) / s4f; one bin of slack either side for the rounding
+        const int b_a = sh.b_lo, b_b = sh.b_hi;
+        if (s4f > 0.f) {
+          const float bw = 4.f / s4f;
+          if (b_a >= 256) {
+            const float d = fmaf((float)(b_a - 269), bw, wlo_f);
+            if (d > 0.f) lo2 = max(lo, __float_as_uint(d));
+          }
+          if (b_b >= 256) {
+            const float d = fmaf((float)(b_b - 266), bw, wlo_f);
+            if (d > 0.f) hi2 = min(hi, __float_as_uint(d));
           }
         }
+        lo2 = min(lo2, hi);
+        hi2 = max(hi2, lo2);
       }
+      TILE_T(5);
+      // ---- pass B: count the keys under lo2, collect the keys of [lo2, hi2], select ----------------------------------------
+      // (not resolved here: the narrow bracket missed the rank -- 3.5 sigma, a few boxes per ten thousand --, the strips hold more keys
+      //  of the coarse bracket than the capture buffer, a collect column ran over, or ties: lift_block_kernel finishes the box)
+      int why = 4;
+      if (ncap <= kTileStripCap) why = tile_count_select(fbase, W, n_scan, lo2, hi2 - lo2, r - below_tiles - strips_below, two ? 1 : 0);
+      TILE_T(7);
+      handover = why != 0;
+#ifdef LM3D_DEBUG_REASONS
+      if (tid == 0) { atomicAdd(&A.counters[16 + why], 1); atomicAdd(&A.counters[22], sh.ncoll); atomicAdd(&A.counters[23], n_scan); atomicAdd(&A.counters[21], min(ncap, 4096)); }
+#endif
+      k0 = sh.sel[0];
+      k1 = two ? sh.sel[1] : k0;
     }
     if (handover) {
       if (tid == 0) {

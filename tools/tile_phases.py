@@ -7,7 +7,7 @@ import torch
 from lm3d import _capi, lift, synth
 dev = torch.device("cuda:0")
 lib = _capi.load()
-NAMES = ["setup", "bracket", "classify", "strips1", "scan1", "reduce+bins", "strips2", "scan2", "sort+write", "claim"]
+NAMES = ["setup", "bracket", "-", "tiles+strips", "passA", "narrow", "-", "passB", "select+write", "claim"]
 for name, F in (("C3", int(sys.argv[1]) if len(sys.argv) > 1 else 128), ("C5", int(sys.argv[2]) if len(sys.argv) > 2 else 64)):
     _, H, W, B = synth.CONFIGS[name]
     d = synth.make_sequence_torch(F, H, W, B, seed=1234 + int(name[1:]), device=dev)
