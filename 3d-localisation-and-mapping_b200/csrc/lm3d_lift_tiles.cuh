@@ -17,7 +17,7 @@
 //                         pixel by pixel ONCE: reduce, count the keys under lo, capture the keys inside [lo, hi];
 //                       * pass A: a quarter of the pixels of every listed tile (4 of its 16 rows) goes through the bracket
 //                         histogram (1000 bins across [lo, hi]); the scaled counts give a NARROW bracket [lo', hi'] around
-//                         the rank -- +-3.5 sigma of the sampling error: ~1500 keys of a 173 k-pixel box;
+//                         the rank -- +-3 sigma of the sampling error: ~1500 keys of a 173 k-pixel box;
 //                       * pass B: every pixel of the listed tiles, in key space and without any shared-memory traffic but
 //                         the rare hits: count the valid keys under lo' (one subtract, one compare, one predicated add per
 //                         pixel), append the keys inside [lo', hi'] to the collect buffer; the captured strip keys likewise;
@@ -47,18 +47,21 @@ constexpr int kTileQuads = kTile * kTile / 4;  // float4 quads per tile (64)
 #endif
 constexpr int kTileMaxInt = LM3D_TILE_MAXINT;  // completely covered tiles per box the scan list holds
 constexpr int kTileListPad = 32;             // zero offsets behind the list: the batched loads may run past its end
-constexpr int kTileColRows = 40;             // collect columns: rows of 256 words (a thread appends its hits to its own column)
+#ifndef LM3D_TILE_COLROWS
+#define LM3D_TILE_COLROWS 40
+#endif
+constexpr int kTileColRows = LM3D_TILE_COLROWS;             // collect columns: rows of 256 words (a thread appends its hits to its own column)
 constexpr int kTileStripCap = 24 * 256;      // strip keys inside the coarse bracket pass 1 may capture (the capture buffer underlies the columns)
 constexpr int kTileStride = 4;               // pass A looks at one pixel row in four of every listed tile
 #ifndef LM3D_TILE_NARROW_Z
-#define LM3D_TILE_NARROW_Z 3.5f
+#define LM3D_TILE_NARROW_Z 3.0f
 #endif
 constexpr float kTileNarrowZ = LM3D_TILE_NARROW_Z;  // half-width of the narrow bracket in sigmas of pass A's sampling error
 #ifndef LM3D_TILE_PREFETCH
-#define LM3D_TILE_PREFETCH 1       // 1: the strips' cache lines are requested into L2 (prefetch.global.L2) while the bracket is being found
+#define LM3D_TILE_PREFETCH 0       // 1: the strips' cache lines are requested into L2 (prefetch.global.L2) while the bracket is being found
 #endif
 #ifndef LM3D_TILE_SAMPLE
-#define LM3D_TILE_SAMPLE 2048
+#define LM3D_TILE_SAMPLE 1024   // (C3 / C5: 2048 samples 17.7 / 28.2 ms, 1024 17.2 / 28.0, 512 17.5 / 29.2 with four times the hand-overs)
 #endif
 constexpr int kTileSample = LM3D_TILE_SAMPLE;  // lattice sample per box
 #ifndef LM3D_TILE_BRACKET_Z
@@ -110,16 +113,21 @@ __device__ __forceinline__ FrameTab load_tab(const FrameTab* tab, int f) {
 //     next three loads (L1), DRAM traffic is the frame once.
 // ------------------------------------------------------------------------------------------
 constexpr int kTileSumThreads = 128;
+__device__ __forceinline__ void tile_sum_one(const float* __restrict__ depth, int H, int W, const FrameTab* __restrict__ tab, uint32_t dmax_bits,
+                                             int f, int ntx, int tile, TileSum* __restrict__ out);
 __global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArgs T) {
   const int slot = blockIdx.y, f = T.f0 + slot;
   if (T.frame_area[f] < T.area_thr) return;  // frame under the cover threshold: lift_block_kernel has its boxes
   const int n_tiles = T.ntx * T.nty;
   const int tile = blockIdx.x * kTileSumThreads + threadIdx.x;
   if (tile >= n_tiles) return;
-  const int W = T.A.W;
-  const int ty = tile / T.ntx, tx = tile - ty * T.ntx;
-  const float* __restrict__ p = T.A.depth + (size_t)f * T.A.H * W + (size_t)(ty * kTile) * W + tx * kTile;
-  const FrameTab tb = load_tab(T.A.tab, f);
+  tile_sum_one(T.A.depth, T.A.H, T.A.W, T.A.tab, T.A.dmax_bits, f, T.ntx, tile, T.tsum + (size_t)slot * n_tiles + tile);
+}
+__device__ __forceinline__ void tile_sum_one(const float* __restrict__ depth, int H, int W, const FrameTab* __restrict__ tab, uint32_t dmax_bits,
+                                             int f, int ntx, int tile, TileSum* __restrict__ out) {
+  const int ty = tile / ntx, tx = tile - ty * ntx;
+  const float* __restrict__ p = depth + (size_t)f * H * W + (size_t)(ty * kTile) * W + tx * kTile;
+  const FrameTab tb = load_tab(tab, f);
   const float uc = (float)(tx * kTile) + 7.5f, vc = (float)(ty * kTile) + 7.5f;
   float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
   float dmn = INFINITY, dmx = -INFINITY, s0 = 0.f, su = 0.f, sv = 0.f, nv = 0.f, rawmx = -INFINITY;
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArg
         float d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool v = key_valid(bits[j], T.A.dmax_bits);
+          const bool v = key_valid(bits[j], dmax_bits);
           d[j] = __uint_as_float(v ? bits[j] : 0x7fffffffu);  // NaN: dropped by the 3-input min / max
           if (v) { nv += 1.0f; s0 += __uint_as_float(bits[j]); su = fmaf(du + (float)j, __uint_as_float(bits[j]), su); sv = fmaf(vr, __uint_as_float(bits[j]), sv); }
         }
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArg
       }
     }
   }
-  float4* o = reinterpret_cast<float4*>(T.tsum + (size_t)slot * n_tiles + tile);
+  float4* o = reinterpret_cast<float4*>(out);
   o[0] = make_float4(__int_as_float((int)nv), s0, su, sv);
   o[1] = make_float4(mn0, mn1, mn2, mx0);
   o[2] = make_float4(mx1, mx2, dmn, dmx);
@@ -189,6 +197,7 @@ struct TileBoxShared {
   int b_lo, b_hi, before, end, ncoll, item, n_scan, ncap, nsmall;
   uint32_t sel[2];
   int sr[4][4], n_sr;            // boundary strips {x0, y0, x1, y1}
+  int sg[4][4];                  // their thread geometry {P | Qp << 8, RPq, nsteps, ceil(65536 / Qp)}, worked out once by thread 0
   int tx_lo, ty_lo, ntx_i, n_int;  // completely covered tiles: origin, tiles per row, count
 };
 // dynamic shared memory (words): histogram | collect columns (first: strip capture) | scan list (+ pad) | TileBoxShared
@@ -246,19 +255,18 @@ __device__ __forceinline__ void accum_quad_strip(const uint4 q, const uint32_t (
 }
 
 // the single pass over one boundary strip {rx0, ry0, rx1, ry1}
-__device__ __forceinline__ void tile_strip_pass(const float* __restrict__ fbase, int W, int rx0, int ry0, int rx1, int ry1, uint32_t dmax_bits,
-                                                const FrameTab& tb, float uc, float vc, AccQ& acc, float& s0_all, float& su, uint32_t lo,
-                                                uint32_t cbelow, uint32_t dspan, int& n_below, uint32_t* capbuf, int* ncap) {
+__device__ __forceinline__ void tile_strip_pass(const float* __restrict__ fbase, int W, int rx0, int ry0, int rx1, int ry1, const int (&sg)[4],
+                                                uint32_t dmax_bits, const FrameTab& tb, float uc, float vc, AccQ& acc, float& s0_all, float& su,
+                                                uint32_t lo, uint32_t cbelow, uint32_t dspan, int& n_below, uint32_t* capbuf, int* ncap) {
   const int tid = threadIdx.x;
   const int rh = ry1 - ry0 + 1;
   const int xa = rx0 & ~3;
   const int Q = (rx1 - xa + 4) >> 2;
-  const int P = (Q + kBlkThreads - 1) / kBlkThreads;
-  const int Qp = (Q + P - 1) / P;
-  const int RPq = kBlkThreads / Qp;
-  const int tr = tid / Qp, tq = tid - tr * Qp;
+  // Q quads per row in P column passes of Qp <= 256 quads, RPq = 256 / Qp rows per step (thread 0 did the divisions: four per strip
+  // and warp were a tenth of the kernel's instructions)
+  const int P = sg[0] & 0xff, Qp = sg[0] >> 8, RPq = sg[1], nsteps = sg[2];
+  const int tr = (tid * sg[3]) >> 16, tq = tid - tr * Qp;  // tid / Qp (exact for tid < 256)
   const bool active = tr < RPq;
-  const int nsteps = (rh + RPq - 1) / RPq;
   const uint32_t rstep = (uint32_t)(RPq * W);
   const float frp = (float)RPq;
   for (int p = 0; p < P; ++p) {
@@ -374,8 +382,8 @@ __device__ __noinline__ void tile_pass1_sums(const float* __restrict__ fbase, in
     const int n_sr = sh.n_sr;
 #pragma unroll 1
     for (int s = 0; s < n_sr; ++s)
-      tile_strip_pass(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], dmax_bits, tb, uc, vc, acc, s0_all, su, lo, 1u - lo, hi - lo,
-                      sb_t, smem_u32 + kTileOffCap, &sh.ncap);
+      tile_strip_pass(fbase, W, sh.sr[s][0], sh.sr[s][1], sh.sr[s][2], sh.sr[s][3], sh.sg[s], dmax_bits, tb, uc, vc, acc, s0_all, su, lo, 1u - lo,
+                      hi - lo, sb_t, smem_u32 + kTileOffCap, &sh.ncap);
   }
   const int nv_strips_l = (int)acc.n_valid;
   const double d0 = warp_sum_d(ds0 + (double)s0_all), d1 = warp_sum_d(dsu + (double)su), d2 = warp_sum_d(dsv + (double)acc.sv);
@@ -496,8 +504,11 @@ __device__ __noinline__ int tile_count_select(const float* __restrict__ fbase, i
   }
   {
     const uint32_t* scan_list = smem_u32 + kTileOffList + (tid >> 6);  // the 64-thread group takes tiles g, g + 4, g + 8, ...
-    const float* __restrict__ qp = fbase + (((tid & 63) >> 2) * W + (tid & 3) * 4);  // (row, quad column) inside a tile
     const int n_my = (n_scan - (tid >> 6) + 3) >> 2;     // (same for the 64 threads of a group: warp-uniform control)
+    // (A per-tile rotation of the thread's position inside the tile, (t + 21 m) & 63, was measured against grid-aligned features
+    // overfilling single columns: 3 % slower, same hand-over count -- the rare overflows are not a clustering effect.)
+    const float* __restrict__ qp = fbase + (((tid & 63) >> 2) * W + (tid & 3) * 4);  // (row, quad column) inside a tile
+    auto load = [&](int m, int) { return ldg_u4(qp + scan_list[4 * m]); };
     auto quad = [&](const uint4 q) {
       tile_count_key(q.x, lo2, cbelow2, dspan2, n_below, ptr);
       tile_count_key(q.y, lo2, cbelow2, dspan2, n_below, ptr);
@@ -508,17 +519,17 @@ __device__ __noinline__ int tile_count_select(const float* __restrict__ fbase, i
     // (the list is padded with kTileListPad zero offsets: requests past the end read the frame's first tile and are dropped)
     uint4 qa[4], qb[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * i]);
+    for (int i = 0; i < 4; ++i) qa[i] = load(i, i);
 #pragma unroll 1
     for (int m0 = 0; m0 < n_my; m0 += 8) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qb[i] = ldg_u4(qp + scan_list[4 * (m0 + 4 + i)]);
+      for (int i = 0; i < 4; ++i) qb[i] = load(m0 + 4 + i, 4 + i);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (m0 + i < n_my) quad(qa[i]);
       if (m0 + 4 >= n_my) break;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(qp + scan_list[4 * (m0 + 8 + i)]);
+      for (int i = 0; i < 4; ++i) qa[i] = load(m0 + 8 + i, i);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (m0 + 4 + i < n_my) quad(qb[i]);
@@ -616,6 +627,10 @@ __device__ unsigned long long g_tile_prof[16];
 #else
 #define TILE_T(ph) do { } while (0)
 #endif
+// (Measured and dropped: building the NEXT chunk's summaries inside this grid, as a second kind of work item spread between the
+// boxes, so that the HBM-bound summaries overlap the box phases.  C3 x 2000 frames 15.7 -> 16.4 ms, C5 x 1000 26.9 -> 27.4: a CTA that
+// summarises tiles has a third of the loads in flight of tile_sum_kernel's 28 warps per SM, the summaries take 3 x longer and the
+// overlap does not pay for it.)
 #ifndef LM3D_TILE_MINB
 #define LM3D_TILE_MINB 3   // 3 x 256 threads at 80 registers; 4 x 64 registers measured equal (the kernel is bound by the SM's throughput, not by latency)
 #endif
@@ -656,7 +671,12 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       const int ntx_i = has_int ? tx_hi - tx_lo + 1 : 0, nty_i = has_int ? ty_hi - ty_lo + 1 : 0;
       sh.tx_lo = tx_lo; sh.ty_lo = ty_lo; sh.ntx_i = ntx_i; sh.n_int = ntx_i * nty_i;
       int n_sr = 0;
-      auto strip = [&](int x0, int y0, int x1, int y1) { sh.sr[n_sr][0] = x0; sh.sr[n_sr][1] = y0; sh.sr[n_sr][2] = x1; sh.sr[n_sr][3] = y1; ++n_sr; };
+      auto strip = [&](int x0, int y0, int x1, int y1) {
+        sh.sr[n_sr][0] = x0; sh.sr[n_sr][1] = y0; sh.sr[n_sr][2] = x1; sh.sr[n_sr][3] = y1;
+        const int Q = (x1 - (x0 & ~3) + 4) >> 2, P = (Q + kBlkThreads - 1) / kBlkThreads, Qp = (Q + P - 1) / P, RPq = kBlkThreads / Qp;
+        sh.sg[n_sr][0] = P | (Qp << 8); sh.sg[n_sr][1] = RPq; sh.sg[n_sr][2] = (y1 - y0 + RPq) / RPq; sh.sg[n_sr][3] = (65536 + Qp - 1) / Qp;
+        ++n_sr;
+      };
       if (!has_int) {
         n_sr = -1;  // no completely covered tile (or more than the list holds): nothing to gain here, lift_block_kernel takes the box
       } else {
@@ -793,7 +813,7 @@ __global__ void __launch_bounds__(kBlkThreads, LM3D_TILE_MINB) tile_box_kernel(c
       }
       TILE_T(5);
       // ---- pass B: count the keys under lo2, collect the keys of [lo2, hi2], select ----------------------------------------
-      // (not resolved here: the narrow bracket missed the rank -- 3.5 sigma, a few boxes per ten thousand --, the strips hold more keys
+      // (not resolved here: the narrow bracket missed the rank -- 3 sigma, a few boxes per thousand --, the strips hold more keys
       //  of the coarse bracket than the capture buffer, a collect column ran over, or ties: lift_block_kernel finishes the box)
       int why = 4;
       if (ncap <= kTileStripCap) why = tile_count_select(fbase, W, n_scan, lo2, hi2 - lo2, r - below_tiles - strips_below, two ? 1 : 0);

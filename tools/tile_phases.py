@@ -7,7 +7,7 @@ import torch
 from lm3d import _capi, lift, synth
 dev = torch.device("cuda:0")
 lib = _capi.load()
-NAMES = ["setup", "bracket", "-", "tiles+strips", "passA", "narrow", "-", "passB", "select+write", "claim"]
+NAMES = ["setup", "bracket", "-", "tiles+strips", "passA", "narrow", "-", "passB", "select+write", "claim", "sum items"]
 for name, F in (("C3", int(sys.argv[1]) if len(sys.argv) > 1 else 128), ("C5", int(sys.argv[2]) if len(sys.argv) > 2 else 64)):
     _, H, W, B = synth.CONFIGS[name]
     d = synth.make_sequence_torch(F, H, W, B, seed=1234 + int(name[1:]), device=dev)
@@ -24,7 +24,7 @@ for name, F in (("C3", int(sys.argv[1]) if len(sys.argv) > 1 else 128), ("C5", i
     e1.record()
     torch.cuda.synchronize()
     lib.lm3d_debug_tile_prof(out, 0)
-    tot = sum(out[:10])
+    tot = sum(out[:11])
     print(f"{name} F={F} boxes={F*B} lift_ms={e0.elapsed_time(e1):.3f} cycles/box={tot/(F*B):.0f}")
     for i, n in enumerate(NAMES):
         print(f"  {n:12s} {100.0*out[i]/tot:5.1f} %   {out[i]/(F*B):9.0f} cycles/box")
