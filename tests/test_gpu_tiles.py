@@ -163,3 +163,54 @@ def test_tile_path_small_workspace_degrades_to_blocks(cuda_device):
     assert c[14] == 0 and c[1] == rect4.shape[0]
     want = ora.lift_boxes(seq.depth, seq.pose7, seq.intr4_depth_res(), rect4.cpu().numpy(), seq.frame_off())
     assert_records_match(lift.records_to_numpy(rec), os_.cpu().numpy(), want)
+
+
+def test_tile_path_over_range_and_garbage_pixels(cuda_device):
+    """max_depth cuts into the boxes (the listed tiles hold over-range pixels: pass A takes its validity-testing form) and
+    10 % of the pixels are 0 / negative / NaN / +-inf: the key-space tests of pass B and of the strips must drop all of
+    them without a validity test."""
+    from lm3d import synth
+
+    seq = synth.make_config("C3", frames=1)
+    rng = np.random.default_rng(5)
+    r = rng.random(seq.depth.shape)
+    d = seq.depth
+    d[r < 0.02] = -d[r < 0.02]
+    d[(r >= 0.02) & (r < 0.04)] = np.inf
+    d[(r >= 0.04) & (r < 0.06)] = -np.inf
+    d[(r >= 0.06) & (r < 0.08)] = -0.0
+    d[(r >= 0.08) & (r < 0.10)] = np.nan
+    for max_depth in (float("inf"), 2400.0, 1700.0):
+        rec, os_, want, counters = lift_with_plan(seq, cuda_device, max_depth_mm=max_depth)
+        assert_records_match(rec, os_, want)
+        assert counters[14] < 0.2 * len(want), (max_depth, counters[14])
+
+
+def test_tile_path_constant_plane_hands_over_exactly(cuda_device):
+    """Every key of a box ties: the strips alone hold more keys of the (degenerate) bracket than the capture buffer, the
+    columns would overflow -- the boxes go to lift_block_kernel, the records stay exact."""
+    from lm3d import synth
+
+    seq = synth.make_config("C3", frames=1)
+    seq.depth[...] = 1234.5
+    seq.depth[0, ::7, ::5] = 0.0
+    rec, os_, want, counters = lift_with_plan(seq, cuda_device)
+    assert_records_match(rec, os_, want)
+    assert counters[14] > 0
+
+
+@pytest.mark.parametrize("chunk", [1, 2])
+def test_tile_path_frame_chunks(cuda_device, monkeypatch, chunk):
+    """Five frames in chunks of 1 / 2 (the TileSum scratch is reused chunk after chunk): same records as the oracle."""
+    monkeypatch.setenv("LM3D_TILE_PATH", "on")
+    monkeypatch.setenv("LM3D_TILE_COVER", "0.01")
+    monkeypatch.setenv("LM3D_TILE_CHUNK", str(chunk))
+    H, W = 200, 168
+    rng = np.random.default_rng(77)
+    depth = (900 + 700 * rng.random((5, H, W)) + 0.5 * np.arange(W)[None, None, :]).astype(np.float32)
+    depth[rng.random(depth.shape) < 0.03] = 0.0
+    rects = _alignment_rects(H, W)[:6]
+    seq = make_seq(depth, len(rects))
+    rec, os_, want, counters = lift_with_plan(seq, cuda_device, rect4=rects * 5)
+    assert_records_match(rec, os_, want)
+    assert counters[14] < len(rects) * 5
