@@ -112,10 +112,18 @@ __device__ __forceinline__ FrameTab load_tab(const FrameTab* tab, int f) {
 //     frame).  A lane's 16-byte loads sit 64 bytes from its neighbours': every sector fetched is used by the lane's
 //     next three loads (L1), DRAM traffic is the frame once.
 // ------------------------------------------------------------------------------------------
+#ifndef LM3D_TILE_SUM_PIPE
+#define LM3D_TILE_SUM_PIPE 0   // 1: software pipeline (the next row's loads in flight while a row is reduced): 82 registers, 6 CTAs per SM.  Measured on
+                               // 256 frames of 1920 x 1440: two rows at a time at 76 registers (6 CTAs) 589 us, pipelined 533 us, two rows at a time
+                               // capped at 72 registers (7 CTAs, the default) best in the whole step (C3 x 1024 frames: 8.55 / 8.35 / 8.25 ms)
+#endif
 constexpr int kTileSumThreads = 128;
 __device__ __forceinline__ void tile_sum_one(const float* __restrict__ depth, int H, int W, const FrameTab* __restrict__ tab, uint32_t dmax_bits,
                                              int f, int ntx, int tile, TileSum* __restrict__ out);
-__global__ void __launch_bounds__(kTileSumThreads) tile_sum_kernel(const TileArgs T) {
+#ifndef LM3D_TILE_SUM_MINB
+#define LM3D_TILE_SUM_MINB 7
+#endif
+__global__ void __launch_bounds__(kTileSumThreads, LM3D_TILE_SUM_MINB) tile_sum_kernel(const TileArgs T) {
   const int slot = blockIdx.y, f = T.f0 + slot;
   if (T.frame_area[f] < T.area_thr) return;  // frame under the cover threshold: lift_block_kernel has its boxes
   const int n_tiles = T.ntx * T.nty;
@@ -134,46 +142,67 @@ __device__ __forceinline__ void tile_sum_one(const float* __restrict__ depth, in
   // ray term of pixel (u, v): g_k = a_k u + b_k v + c_k, walked along a row in pairs: (g, g + a_k) += 2 a_k
   const f32x2 step0 = pack2(2.f * tb.a[0], 2.f * tb.a[0]), step1 = pack2(2.f * tb.a[1], 2.f * tb.a[1]), step2 = pack2(2.f * tb.a[2], 2.f * tb.a[2]);
   const float u0 = (float)(tx * kTile);
-#pragma unroll 1
-  for (int r0 = 0; r0 < kTile; r0 += 2) {  // two rows = eight 16-byte loads in flight
-    uint4 q[8];
+  // one pixel row of the tile (four quads)
+  auto row = [&](const uint4 (&q)[4], int r) {
+    const float vf = (float)(ty * kTile + r);
+    const float vr = vf - vc;
+    const float b0 = fmaf(tb.b[0], vf, fmaf(tb.a[0], u0, tb.c[0])), b1 = fmaf(tb.b[1], vf, fmaf(tb.a[1], u0, tb.c[1])),
+                b2 = fmaf(tb.b[2], vf, fmaf(tb.a[2], u0, tb.c[2]));
+    f32x2 g0 = pack2(b0, b0 + tb.a[0]), g1 = pack2(b1, b1 + tb.a[1]), g2 = pack2(b2, b2 + tb.a[2]);
+    float du = u0 - uc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = ldg_u4(p + (size_t)(r0 + (i >> 2)) * W + (i & 3) * 4);
+    for (int qi = 0; qi < 4; ++qi) {
+      const uint4 qq = q[qi];
+      const uint32_t bits[4] = {qq.x, qq.y, qq.z, qq.w};
+      float d[4];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const float vf = (float)(ty * kTile + r0 + rr);
-      const float vr = vf - vc;
-      const float b0 = fmaf(tb.b[0], vf, fmaf(tb.a[0], u0, tb.c[0])), b1 = fmaf(tb.b[1], vf, fmaf(tb.a[1], u0, tb.c[1])),
-                  b2 = fmaf(tb.b[2], vf, fmaf(tb.a[2], u0, tb.c[2]));
-      f32x2 g0 = pack2(b0, b0 + tb.a[0]), g1 = pack2(b1, b1 + tb.a[1]), g2 = pack2(b2, b2 + tb.a[2]);
-      float du = u0 - uc;
+      for (int j = 0; j < 4; ++j) {
+        const bool v = key_valid(bits[j], dmax_bits);
+        d[j] = __uint_as_float(v ? bits[j] : 0x7fffffffu);  // NaN: dropped by the 3-input min / max
+        if (v) { nv += 1.0f; s0 += __uint_as_float(bits[j]); su = fmaf(du + (float)j, __uint_as_float(bits[j]), su); sv = fmaf(vr, __uint_as_float(bits[j]), sv); }
+      }
+      du += 4.f;
 #pragma unroll
-      for (int qi = 0; qi < 4; ++qi) {
-        const uint4 qq = q[rr * 4 + qi];
-        const uint32_t bits[4] = {qq.x, qq.y, qq.z, qq.w};
-        float d[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool v = key_valid(bits[j], dmax_bits);
-          d[j] = __uint_as_float(v ? bits[j] : 0x7fffffffu);  // NaN: dropped by the 3-input min / max
-          if (v) { nv += 1.0f; s0 += __uint_as_float(bits[j]); su = fmaf(du + (float)j, __uint_as_float(bits[j]), su); sv = fmaf(vr, __uint_as_float(bits[j]), sv); }
-        }
-        du += 4.f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const f32x2 dp = pack2(d[2 * h], d[2 * h + 1]);
-          float xa, xb;
-          unpack2(mul2(dp, g0), xa, xb); mn0 = fmin3(mn0, xa, xb); mx0 = fmax3(mx0, xa, xb);
-          unpack2(mul2(dp, g1), xa, xb); mn1 = fmin3(mn1, xa, xb); mx1 = fmax3(mx1, xa, xb);
-          unpack2(mul2(dp, g2), xa, xb); mn2 = fmin3(mn2, xa, xb); mx2 = fmax3(mx2, xa, xb);
-          g0 = add2(g0, step0); g1 = add2(g1, step1); g2 = add2(g2, step2);
-          dmn = fmin3(dmn, d[2 * h], d[2 * h + 1]);
-          dmx = fmax3(dmx, d[2 * h], d[2 * h + 1]);
-          rawmx = fmax3(rawmx, __uint_as_float(bits[2 * h]), __uint_as_float(bits[2 * h + 1]));
-        }
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 dp = pack2(d[2 * h], d[2 * h + 1]);
+        float xa, xb;
+        unpack2(mul2(dp, g0), xa, xb); mn0 = fmin3(mn0, xa, xb); mx0 = fmax3(mx0, xa, xb);
+        unpack2(mul2(dp, g1), xa, xb); mn1 = fmin3(mn1, xa, xb); mx1 = fmax3(mx1, xa, xb);
+        unpack2(mul2(dp, g2), xa, xb); mn2 = fmin3(mn2, xa, xb); mx2 = fmax3(mx2, xa, xb);
+        g0 = add2(g0, step0); g1 = add2(g1, step1); g2 = add2(g2, step2);
+        dmn = fmin3(dmn, d[2 * h], d[2 * h + 1]);
+        dmx = fmax3(dmx, d[2 * h], d[2 * h + 1]);
+        rawmx = fmax3(rawmx, __uint_as_float(bits[2 * h]), __uint_as_float(bits[2 * h + 1]));
       }
     }
+  };
+#if LM3D_TILE_SUM_PIPE
+  // software pipeline: the loads of the next row are in flight while this row is reduced (ncu on the two-rows-at-a-time form: 66 % of
+  // the stall samples wait for the first use of a loaded quad, and the warps of a CTA run their load and compute phases in step)
+  uint4 qa[4], qb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(p + i * 4);
+#pragma unroll 1
+  for (int r0 = 0; r0 < kTile; r0 += 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qb[i] = ldg_u4(p + (size_t)(r0 + 1) * W + i * 4);
+    row(qa, r0);
+    if (r0 + 2 < kTile) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = ldg_u4(p + (size_t)(r0 + 2) * W + i * 4);
+    }
+    row(qb, r0 + 1);
   }
+#else
+#pragma unroll 1
+  for (int r0 = 0; r0 < kTile; r0 += 2) {  // two rows = eight 16-byte loads in flight
+    uint4 qa[4], qb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qa[i] = ldg_u4(p + (size_t)r0 * W + i * 4); qb[i] = ldg_u4(p + (size_t)(r0 + 1) * W + i * 4); }
+    row(qa, r0);
+    row(qb, r0 + 1);
+  }
+#endif
   float4* o = reinterpret_cast<float4*>(out);
   o[0] = make_float4(__int_as_float((int)nv), s0, su, sv);
   o[1] = make_float4(mn0, mn1, mn2, mx0);

@@ -8,7 +8,7 @@ REP=r2_prof_$TAG.ncu-rep
 ncu -i $REP --page raw --csv 2>/dev/null > raw_$TAG.csv
 ncu -i $REP --page source --csv --print-source sass 2>/dev/null > sass_$TAG.csv
 ncu -i $REP --page source --csv --print-source cuda 2>/dev/null > src_$TAG.csv
-SHA=$(python -c "import bench; print(bench.source_sha())")
+SHA=$(cd /root/repo && python -c "import bench; print(bench.source_sha())")
 OUT=/root/repo/profiles/r2_${TAG}_ncu_summary.txt
 echo "# ncu --set full --clock-control none --import-source on -k regex:${KERN}, round-2 final build (csrc sha $SHA)" > $OUT
 echo "# $CMD" >> $OUT
