@@ -2,6 +2,7 @@
 # dev helper (run under gpurun, one GPU): the round's N=1 evidence -- full bench line, launch lists, ncu --set full captures
 set -x
 O=gpurun_out
+timeout 300 python -m pytest tests/test_gpu_tiles.py tests/test_gpu_fuzz.py tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -3 > $O/r2_final_tests.log
 (time timeout 900 python bench.py) > $O/r2_bench_n1.json 2> $O/r2_bench_n1.err
 timeout 120 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference_arm.json 2>> $O/r2_bench_n1.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tile_|lift_|prep_|scale_boxes" -c 200 --csv --log-file $O/r2_launches_c2.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-other --no-dropin > $O/r2_ncu_c2.log 2>&1
