@@ -74,6 +74,76 @@ def test_fuzz_against_oracle(cuda_device, case):
     assert_records_match(rec, os_, want)
 
 
+@st.composite
+def tile_cases(draw):
+    H = draw(st.sampled_from([48, 64, 100, 131, 160, 200]))
+    W = draw(st.sampled_from([48, 64, 100, 128, 192, 256]))
+    F = draw(st.integers(1, 3))
+    seed = draw(st.integers(0, 2**31 - 1))
+    q = draw(st.sampled_from([0.0, 5.0, 25.0, 50.0, 50.0, 61.8, 99.0, 100.0]))
+    p_zero = draw(st.sampled_from([0.0, 0.02, 0.3, 0.9]))
+    p_bad = draw(st.sampled_from([0.0, 0.001, 0.05]))
+    step = draw(st.sampled_from([0.0, 0.0, 0.0, 0.5, 7.0, 300.0]))
+    patch = draw(st.booleans())
+    n_boxes = draw(st.lists(st.integers(0, 5), min_size=F, max_size=F))
+    rects = []
+    for f in range(F):
+        for _ in range(n_boxes[f]):
+            xa, xb = sorted((draw(st.integers(0, W - 1)), draw(st.integers(0, W - 1))))
+            ya, yb = sorted((draw(st.integers(0, H - 1)), draw(st.integers(0, H - 1))))
+            xa, xb, ya, yb = xa // 3, W - 1 - (W - 1 - xb) // 3, ya // 3, H - 1 - (H - 1 - yb) // 3   # big rects: interior tiles exist
+            rects.append((xa, ya, xb, yb))
+    max_depth = draw(st.sampled_from([float("inf"), 1900.0, 1500.0]))
+    return H, W, F, seed, q, p_zero, p_bad, step, patch, n_boxes, rects, max_depth
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tile_cases())
+def test_fuzz_tile_path_against_oracle(cuda_device, case):
+    """The same draw, forced through the tile path (tile_sum_kernel + tile_box_kernel: sampled histogram, key-space counting):
+    small frames, so a box has a handful of interior tiles and wide strips; flat patches (many keys on a few values), invalid
+    pixels of every kind, quantised depth, max_depth inside the data."""
+    import os
+
+    H, W, F, seed, q, p_zero, p_bad, step, patch, n_boxes, rects, max_depth = case
+    rng = np.random.default_rng(seed)
+    depth = (1200 + 900 * rng.random((F, H, W)) + 2.0 * np.arange(W)[None, None, :]).astype(np.float32)
+    if patch:
+        depth[:, H // 4 : 3 * H // 4, W // 4 : 3 * W // 4] = (1600.0 + 2.0 * rng.standard_normal((F, 3 * H // 4 - H // 4, 3 * W // 4 - W // 4))).astype(np.float32)
+    if step > 0:
+        depth = (np.round(depth / step) * step).astype(np.float32)
+    r = rng.random(depth.shape)
+    depth[r < p_zero] = 0.0
+    bad = r > 1.0 - p_bad
+    depth[bad] = rng.choice(np.array([np.nan, np.inf, -np.inf, -5.0, 1e9], dtype=np.float32), size=int(bad.sum()))
+    frame_off = np.concatenate([[0], np.cumsum(n_boxes)]).astype(np.int64)
+    if not rects:
+        return
+    old = {k: os.environ.get(k) for k in ("LM3D_TILE_PATH", "LM3D_TILE_COVER", "LM3D_TILE_CHUNK")}
+    os.environ.update(LM3D_TILE_PATH="on", LM3D_TILE_COVER="0.01", LM3D_TILE_CHUNK="2")
+    try:
+        rec, os_, want, counters = _lift(cuda_device, depth, rects, frame_off, q, max_depth)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert_records_match(rec, os_, want)
+    assert counters[15] == 0
+    _TILE_FUZZ["large"] += int((want["n_pix"] > 8160).sum())
+    _TILE_FUZZ["handed"] += int(counters[14])
+
+
+_TILE_FUZZ = {"large": 0, "handed": 0}
+
+
+def test_fuzz_tile_path_was_exercised(cuda_device):
+    """(runs after the fuzz above) most CTA-class boxes of the draws were finished by tile_box_kernel itself."""
+    assert _TILE_FUZZ["large"] >= 40, _TILE_FUZZ
+    assert _TILE_FUZZ["handed"] < 0.6 * _TILE_FUZZ["large"], _TILE_FUZZ
+
+
 def _lattice_mask(n_pix, samples):
     idx = (np.arange(samples, dtype=np.int64) * n_pix + (n_pix >> 1)) // samples
     m = np.zeros(n_pix, dtype=bool)
