@@ -59,6 +59,9 @@ constexpr int kQuadSlotsMax = kQuadDepth > kQuadDepth2 ? kQuadDepth : kQuadDepth
 #ifndef LM3D_QUAD_CAPTURE
 #define LM3D_QUAD_CAPTURE 0
 #endif
+#ifndef LM3D_QUAD_WARP_PUSH
+#define LM3D_QUAD_WARP_PUSH 1  // fused gather: 1 = the warp pushes a finished record (96 contiguous bytes per peer), 0 = lane 0 does, 16 bytes at a time
+#endif
 #ifndef LM3D_QUAD_COLL_ROWS
 #define LM3D_QUAD_COLL_ROWS (LM3D_QUAD_CAPTURE ? 44 : 28)
 #endif
@@ -732,11 +735,30 @@ __global__ void __launch_bounds__(kQuadWarps * 32, LM3D_QUAD_MINB) lift_quad_ker
         tb.a[0] = t0.x; tb.a[1] = t0.y; tb.a[2] = t0.z; tb.b[0] = t0.w;
         tb.b[1] = t1.x; tb.b[2] = t1.y; tb.c[0] = t1.z; tb.c[1] = t1.w;
         tb.c[2] = t2.x; tb.t[0] = t2.y; tb.t[1] = t2.z; tb.t[2] = t2.w;
+#if LM3D_QUAD_WARP_PUSH
+        write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
+                         tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
+                         (float)(1.0 / A.scale_depth));
+#else
         write_record_f32(reinterpret_cast<float*>(A.out + b), A.order_stats ? A.order_stats + 2 * (size_t)b : nullptr,
                          tb, rc.x0, rc.y0, rc.x1, rc.y1, uc, vc, S0, SU, SV, mn, mx, n_valid_box, k0, k1, (float)gamma,
                          (float)(1.0 / A.scale_depth), A.peer, A.n_peer, A.peer_off + b);
+#endif
       }
       __syncwarp();
+#if LM3D_QUAD_WARP_PUSH
+      // fused record gather: the WARP pushes the record lane 0 has just written (read back through L2) -- lane 6 p + i stores the
+      // i-th 16 bytes to peer p, five peers per store instruction, 96 contiguous bytes per peer -- instead of lane 0 issuing
+      // six 16-byte stores per peer one after the other (48 store instructions and 48 16-byte NVLink writes per box at 8 ranks)
+      if (A.n_peer > 0) {
+        const int pi = lane / 6, wi = lane - 6 * pi;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(A.out + b) + wi);
+        for (int p0 = 0; p0 < A.n_peer; p0 += 5) {
+          const int p = p0 + pi;
+          if (lane < 30 && p < A.n_peer) reinterpret_cast<float4*>(A.peer[p] + A.peer_off + b)[wi] = v;
+        }
+      }
+#endif
     }
     item_next = __shfl_sync(kFull, item_next, 0);
   }
