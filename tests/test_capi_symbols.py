@@ -46,6 +46,26 @@ def test_version_status_and_workspace(lib):
     assert lib.lm3d_workspace_bytes(-1, 5) == 0
 
 
+def test_lift_workspace_adds_the_tile_scratch(lib, monkeypatch):
+    """lm3d_lift_workspace_bytes = the minimum + per-frame box areas + one cursor per frame chunk + 64-byte summaries of every
+    complete 16 x 16 tile for one chunk of frames (256 by default, LM3D_TILE_CHUNK); small frames and W % 4 != 0 add nothing."""
+    for k in ("LM3D_TILE_PATH", "LM3D_TILE_CHUNK"):
+        monkeypatch.delenv(k, raising=False)
+    F, H, W, B = 1000, 1440, 1920, 50000
+    base = lib.lm3d_workspace_bytes(F, B)
+    full = lib.lm3d_lift_workspace_bytes(F, H, W, B)
+    per_frame = (W // 16) * (H // 16) * 64
+    assert base < full and full % 256 == 0
+    assert 256 * per_frame <= full - base <= 256 * per_frame + 4 * F + 4096
+    assert lib.lm3d_lift_workspace_bytes(F, 192, 256, B) == base           # under 2^18 pixels: no tile path
+    assert lib.lm3d_lift_workspace_bytes(F, H, W + 2, B) == base           # W % 4 != 0
+    assert lib.lm3d_lift_workspace_bytes(10, H, W, B) - lib.lm3d_workspace_bytes(10, B) < 11 * per_frame   # fewer frames than a chunk
+    monkeypatch.setenv("LM3D_TILE_CHUNK", "8")
+    assert 8 * per_frame <= lib.lm3d_lift_workspace_bytes(F, H, W, B) - base <= 8 * per_frame + 8 * F + 4096
+    monkeypatch.setenv("LM3D_TILE_PATH", "off")
+    assert lib.lm3d_lift_workspace_bytes(F, H, W, B) == base
+
+
 def test_argument_validation_happens_before_any_cuda_call(lib):
     # q outside [0,100], bad sizes and null pointers are rejected with LM3D_ERR_BAD_ARG (-1)
     z = ctypes.c_void_p(0)
